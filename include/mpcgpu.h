@@ -1,0 +1,171 @@
+/*
+ * mpcgpu.h -- C ABI of the B200 batched SQP backend for mpc_planner's NLP solve loop.
+ *
+ * This is the drop-in boundary.  Everything below is plain C: pointers, sizes and
+ * PODs; no C++/torch types.  The entry points are what a CUDA branch of the reference's
+ * `MPCPlanner::Solver` (mpc_planner_solver/include/mpc_planner_solver/solver_interface.h:4-12,
+ * acados_solver_interface.h:93-222) binds instead of the generated acados C API
+ * (Solver_acados_create_capsule / _update_params / _solve / ocp_nlp_out_get ...; call sites
+ * mpc_planner_solver/src/acados_solver_interface.cpp:17,33,124-142,149-155,164-195,279-283).
+ *
+ * Data layouts are the reference's own (`AcadosParameters`, acados_solver_interface.h:51-91):
+ *   xinit           [nx]                      initial state
+ *   x0              [(nu+nx)*(N+1)]           warm start, node-major, [u_k ; x_k] per node
+ *   all_parameters  [npar*N]                  stage-major parameter vector
+ *   xtraj           [nx*(N+1)], utraj [nu*N]  output (`AcadosOutput`, :127-147)
+ * A batch is P such problems, concatenated solve-major.
+ *
+ * Return convention of every function: 0 = ok, negative = error (mpcgpu_strerror explains).
+ * Per-solve exit codes follow the reference (`completeOneIteration`,
+ * acados_solver_interface.cpp:197-203): 1 = success, 0 = failure, 2 = max iterations,
+ * 3 = min step, 4 = QP failure.
+ */
+#ifndef MPCGPU_H
+#define MPCGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCGPU_MAX_NZ 9          /* nu + nx upper bound (bicycle: 3 + 6)                       */
+#define MPCGPU_MAX_CON_MODULES 4 /* constraint blocks stacked in one problem                   */
+
+/* Dynamics models, solver_generator/solver_model.py */
+enum mpcgpu_model {
+    MPCGPU_MODEL_UNICYCLE = 0,       /* ContouringSecondOrderUnicycleModel          :193-214, nx=5 nu=2 */
+    MPCGPU_MODEL_UNICYCLE_SLACK = 1, /* ContouringSecondOrderUnicycleModelWithSlack :274-298, nx=6 nu=2 */
+    MPCGPU_MODEL_BICYCLE = 2         /* BicycleModel2ndOrder                        :302-351, nx=6 nu=3 */
+};
+
+/* Path-tracking objective, mpc_planner_modules/scripts */
+enum mpcgpu_objective {
+    MPCGPU_OBJ_CONTOURING = 0,     /* contouring.py:48-98 (MPCC)                                 */
+    MPCGPU_OBJ_CURVATURE_AWARE = 1 /* curvature_aware_contouring.py:48-105 (CA-MPC cost)         */
+};
+
+/* Constraint blocks, in module order (solver_definition.py:36-49) */
+enum mpcgpu_constraint_kind {
+    MPCGPU_CON_LINEAR = 0,    /* guidance_constraints.py:95-110   a1 x + a2 y - b <= 0            */
+    MPCGPU_CON_ELLIPSOID = 1, /* ellipsoid_constraints.py:65-119  d' M d >= 1                     */
+    MPCGPU_CON_GAUSSIAN = 2,  /* gaussian_constraints.py:68-117   chance constraint >= 0          */
+    MPCGPU_CON_DECOMP = 3,    /* decomp_constraints.py:68-98      a.disc - (b + slack) <= 0       */
+    MPCGPU_CON_SCENARIO = 4   /* scenario_constraints.py:64-94    a.disc - (b + slack) <= 0       */
+};
+
+/*
+ * The NLP handed to the solver: what `generate_acados_solver` (solver_generator/
+ * generate_acados_solver.py:68-177) configures, as data.  Parameter indices are positions in
+ * the per-stage parameter vector, in the order `define_parameters` (solver_definition.py:5-16)
+ * registers them (objectives first, then constraints; duplicates registered once,
+ * util/parameters.py:43-44).
+ */
+typedef struct mpcgpu_problem_desc {
+    int model;     /* enum mpcgpu_model */
+    int objective; /* enum mpcgpu_objective */
+    int N;         /* shooting intervals (generate_acados_solver.py:88) */
+    int nx, nu, npar, nh;
+    double dt;     /* integrator_step; tf = N*dt (:143) */
+    int erk_steps; /* sim_method_num_steps = 3 (:150); 4 stages per step (:149) */
+    int n_segments; /* contouring/num_segments */
+
+    /* objective parameter indices (-1 = absent) */
+    int p_acceleration, p_angular_velocity, p_slack, p_velocity, p_reference_velocity;
+    int weigh_velocity; /* 1 if MPCBase weighs v with w_v (v - v_ref)^2 (generate_jackalsimulator_solver.py:49-52) */
+    int p_contour, p_lag;
+    int p_spline; /* first of n_segments x {x_a,x_b,x_c,x_d,y_a,y_b,y_c,y_d,start} (contouring.py:33-44) */
+
+    /* shared constraint parameters */
+    int p_ego_disc_radius, p_ego_disc_offset; /* one disc (n_discs = 1) */
+
+    int n_con_modules;
+    int con_kind[MPCGPU_MAX_CON_MODULES];  /* enum mpcgpu_constraint_kind */
+    int con_count[MPCGPU_MAX_CON_MODULES]; /* rows of h contributed */
+    int con_param[MPCGPU_MAX_CON_MODULES]; /* index of the block's first own parameter */
+
+    /* z = [u; x] box (solver_model.py lower_bound/upper_bound; generate_acados_solver.py:100-107) */
+    double lower_bound[MPCGPU_MAX_NZ], upper_bound[MPCGPU_MAX_NZ];
+
+    /* solver options mirrored from generate_acados_solver.py:143-173 and settings.yaml:14-18 */
+    int n_sqp;          /* acados.iterations (10) */
+    int qp_iter_max;    /* qp_solver_iter_max (50) */
+    double qp_tol;      /* qp_tol (1e-5) */
+    double reg_epsilon; /* MIRROR threshold (acados default 1e-4) */
+    double qp_mu0;      /* IPM initial barrier (HPIPM BALANCE: 1e1) */
+    double qp_thr0;     /* IPM initial slack floor (HPIPM: 1e-1) */
+    double res_eq_fail; /* res_eq above this demotes success (acados_solver_interface.cpp:176-181) */
+} mpcgpu_problem_desc;
+
+/* Per-solve result record (`AcadosInfo`, acados_solver_interface.h:96-125) */
+typedef struct mpcgpu_info {
+    double pobj;    /* ocp_nlp_eval_cost at the final iterate (:167-168) */
+    double res_eq;  /* max dynamics defect at the final iterate */
+    double res_stat_qp; /* last QP: stationarity residual (inf-norm) */
+    double res_comp_qp; /* last QP: complementarity residual (inf-norm) */
+    int exit_code;  /* 1 = success ... (see top) */
+    int qp_status;  /* 0 ok, 2 max iter, 3 min step, 4 NaN (acados numbering) */
+    int sqp_iter;   /* RTI iterations executed */
+    int qp_iter;    /* interior-point iterations executed, summed over the solve */
+} mpcgpu_info;
+
+typedef struct mpcgpu_solver *mpcgpu_handle;
+
+/* Library / device introspection (no GPU needed for the first two) */
+const char *mpcgpu_version(void);
+const char *mpcgpu_strerror(int code);
+int mpcgpu_device_count(void);
+
+/* 1 if a kernel specialisation for this problem was compiled into the library, else 0.
+ * Needs no GPU.  Replaces "does the generated Solver exist" of the reference build. */
+int mpcgpu_problem_supported(const mpcgpu_problem_desc *desc);
+
+/* Create a batched solver for up to max_batch simultaneous solves on CUDA device `device`.
+ * Replaces Solver_acados_create_capsule + Solver_acados_create_with_discretization
+ * (acados_solver_interface.cpp:17,33).  Device buffers are owned by the handle. */
+int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mpcgpu_handle *out);
+int mpcgpu_destroy(mpcgpu_handle h);
+
+/* Host-buffer path (what Solver::solve() uses): upload -> solve -> download, synchronous.
+ *   xinit[P*nx], x0[P*(nu+nx)*(N+1)], params[P*npar*N]  -> xtraj[P*nx*(N+1)], utraj[P*nu*N], info[P]
+ * Replaces initializeOneIteration + n_sqp x solveOneIteration + completeOneIteration
+ * (acados_solver_interface.cpp:86-204) for P solvers at once.  best (may be NULL) receives the
+ * index of the successful solve with the smallest pobj (FindBestPlanner,
+ * mpc_planner_modules/src/guidance_constraints.cpp:416-434), or -1 if none succeeded. */
+int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double *x0,
+                      const double *params, double *xtraj, double *utraj, mpcgpu_info *info,
+                      int *best);
+
+/* Device-buffer path: same arrays already resident in HBM; asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = default stream). */
+int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const double *d_x0,
+                        const double *d_params, double *d_xtraj, double *d_utraj,
+                        mpcgpu_info *d_info, int *d_best, void *stream);
+
+/* Pinned host staging buffers for the host path (optional; plain malloc'd memory also works). */
+int mpcgpu_host_alloc(void **ptr, unsigned long long bytes);
+int mpcgpu_host_free(void *ptr);
+
+/* Kernel launches issued by this handle so far (bench.py reports them). */
+long long mpcgpu_launch_count(mpcgpu_handle h);
+
+/* Average device time (ms, CUDA events on the launching stream) of the SQP kernel over the
+ * launches since the last call; resets the accumulator.  Only counted when timing is enabled. */
+int mpcgpu_set_timing(mpcgpu_handle h, int enabled);
+double mpcgpu_kernel_ms(mpcgpu_handle h, int *n_launches);
+
+/* Debug / parity entry points: evaluate the stage functions and their derivatives on the device
+ * for M independent (z, p[, lam, pi]) samples.  Outputs (any may be NULL):
+ *   cost[M], cost_grad[M*nz], cost_hess[M*nz*nz]   dt-unscaled l(z,p)
+ *   h[M*nh], h_jac[M*nh*nz], h_hess[M*nz*nz]       sum_i lam_i * hess h_i
+ *   xnext[M*nx], AB[M*nx*nz] (d xnext / d [u;x]), dyn_hess[M*nz*nz] = sum_j pi_j * hess xnext_j */
+int mpcgpu_eval_stage(mpcgpu_handle h, int M, const double *z, const double *p, const double *lam,
+                      const double *pi, double *cost, double *cost_grad, double *cost_hess,
+                      double *hval, double *h_jac, double *h_hess, double *xnext, double *AB,
+                      double *dyn_hess);
+
+/* Measure the FP64 FMA peak of the device (dependent-free FMA chains on all SMs); GFLOP/s. */
+double mpcgpu_measure_fp64_gflops(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCGPU_H */
