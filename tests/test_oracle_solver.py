@@ -75,7 +75,9 @@ def test_converged_points_are_kkt_points(seed):
         res = minimize(cost, w0, jac=cost_grad, method="SLSQP", constraints=[dict(type="eq", fun=eq), dict(type="ineq", fun=ineq)],
                        options=dict(maxiter=60, ftol=1e-12))
         # an independent NLP solver started at the oracle's point cannot improve on it
-        assert res.fun == pytest.approx(inf["pobj"], rel=3e-6, abs=1e-7)
+        # the IPM stops at complementarity <= qp_tol = 1e-5 per row: objective gap <= n_active * 1e-5
+        assert res.fun == pytest.approx(inf["pobj"], abs=5e-5)
+        assert res.fun <= inf["pobj"] + 1e-9
         assert np.abs(res.x - w0).max() < 5e-3
         checked += 1
     assert checked >= 1
