@@ -1,0 +1,75 @@
+// emu.cpp -- HOST EMULATION of the CUDA kernel source (TEST INFRASTRUCTURE, not a product path).
+// Compiles mpc_planner_b200/csrc/sqp_core.cuh with g++: every warp phase becomes a sequential
+// loop over 32 lanes and "shared memory" is a heap buffer.  This lets the CPU test-suite exercise
+// the kernel's algorithm (against the oracle) without a GPU.  The shipped library never uses it.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../mpc_planner_b200/csrc/registry.cuh"
+
+using namespace mpcgpu;
+
+template <class CFG>
+static int solve_cfg(const mpcgpu_problem_desc &d, int P, const double *xinit, const double *x0, const double *params,
+                     double *xtraj, double *utraj, mpcgpu_info *info, double *iterates) {
+    typedef SL<CFG> S;
+    const Layout L = make_layout(d);
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU;
+    std::vector<double> sm(S::TOTAL), pt((size_t)d.npar * 32);
+    for (int p = 0; p < P; p++) {
+        const double *par = params + (size_t)p * d.npar * N;
+        std::fill(pt.begin(), pt.end(), 0.0);
+        for (int k = 0; k < N; k++)
+            for (int i = 0; i < d.npar; i++) pt[(size_t)i * 32 + k] = par[(size_t)k * d.npar + i];
+        sqp_solve_warp<CFG>(L, sm.data(), xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt.data(),
+                            xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p,
+                            iterates ? iterates + (size_t)p * d.n_sqp * (N + 1) * NZ : nullptr);
+    }
+    return 0;
+}
+
+extern "C" {
+
+int emu_problem_supported(const mpcgpu_problem_desc *d) {
+#define X(C) \
+    if (config_matches<C>(*d)) return 1;
+    MPCGPU_CONFIG_LIST(X)
+#undef X
+    return 0;
+}
+
+int emu_solve(const mpcgpu_problem_desc *d, int P, const double *xinit, const double *x0, const double *params,
+              double *xtraj, double *utraj, mpcgpu_info *info, double *iterates) {
+#define X(C) \
+    if (config_matches<C>(*d)) return solve_cfg<C>(*d, P, xinit, x0, params, xtraj, utraj, info, iterates);
+    MPCGPU_CONFIG_LIST(X)
+#undef X
+    return -2;
+}
+
+int emu_eval_stage(const mpcgpu_problem_desc *d, int M, const double *z, const double *p, const double *lam,
+                   const double *pi, double *cost, double *cost_grad, double *cost_hess, double *hval, double *h_jac,
+                   double *h_hess, double *xnext, double *AB, double *dyn_hess) {
+    const Layout L = make_layout(*d);
+    const int nz = d->nx + d->nu, nx = d->nx, nh = d->nh, npar = d->npar;
+#define X(C)                                                                                                                \
+    {                                                                                                                       \
+        if (config_matches<C>(*d)) {                                                                                        \
+            for (int m = 0; m < M; m++)                                                                                     \
+                eval_stage_sample<C>(L, z + (size_t)m * nz, p + (size_t)m * npar, lam ? lam + (size_t)m * nh : nullptr,     \
+                                     pi ? pi + (size_t)m * nx : nullptr, cost ? cost + m : nullptr,                         \
+                                     cost_grad ? cost_grad + (size_t)m * nz : nullptr,                                      \
+                                     cost_hess ? cost_hess + (size_t)m * nz * nz : nullptr, hval ? hval + (size_t)m * nh : nullptr, \
+                                     h_jac ? h_jac + (size_t)m * nh * nz : nullptr, h_hess ? h_hess + (size_t)m * nz * nz : nullptr, \
+                                     xnext ? xnext + (size_t)m * nx : nullptr, AB ? AB + (size_t)m * nx * nz : nullptr,     \
+                                     dyn_hess ? dyn_hess + (size_t)m * nz * nz : nullptr);                                  \
+            return 0;                                                                                                       \
+        }                                                                                                                   \
+    }
+    MPCGPU_CONFIG_LIST(X)
+#undef X
+    return -2;
+}
+}
