@@ -1,0 +1,155 @@
+"""ctypes binding of the C ABI (include/mpcgpu.h) of mpc_planner_b200/lib/libmpcgpu.so.
+
+This is the Python face of the product path: there is no CPU fallback.  If the library is missing
+or no CUDA device is present, construction fails loudly."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from .problem import ProblemDesc, ProblemSpec, SolveInfo
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmpcgpu.so")
+_lib = None
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+# every symbol include/mpcgpu.h declares
+EXPORTED_SYMBOLS = [
+    "mpcgpu_version", "mpcgpu_strerror", "mpcgpu_device_count", "mpcgpu_problem_supported", "mpcgpu_create", "mpcgpu_destroy",
+    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
+    "mpcgpu_set_timing", "mpcgpu_kernel_ms", "mpcgpu_eval_stage", "mpcgpu_measure_fp64_gflops",
+]
+
+
+class MpcGpuError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the CUDA library (never builds, never falls back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpcGpuError(f"{LIB_PATH} is missing: build it with `python -m mpc_planner_b200.build` (there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mpcgpu_version.restype = ctypes.c_char_p
+    lib.mpcgpu_strerror.restype = ctypes.c_char_p
+    lib.mpcgpu_strerror.argtypes = [ctypes.c_int]
+    lib.mpcgpu_device_count.restype = ctypes.c_int
+    lib.mpcgpu_problem_supported.argtypes = [ctypes.POINTER(ProblemDesc)]
+    lib.mpcgpu_create.argtypes = [ctypes.POINTER(ProblemDesc), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.mpcgpu_destroy.argtypes = [ctypes.c_void_p]
+    lib.mpcgpu_solve_host.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, ctypes.POINTER(SolveInfo), _ip]
+    lib.mpcgpu_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 8
+    lib.mpcgpu_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_ulonglong]
+    lib.mpcgpu_host_free.argtypes = [ctypes.c_void_p]
+    lib.mpcgpu_launch_count.restype = ctypes.c_longlong
+    lib.mpcgpu_launch_count.argtypes = [ctypes.c_void_p]
+    lib.mpcgpu_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.mpcgpu_kernel_ms.restype = ctypes.c_double
+    lib.mpcgpu_kernel_ms.argtypes = [ctypes.c_void_p, _ip]
+    lib.mpcgpu_eval_stage.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_dp] * 13
+    lib.mpcgpu_measure_fp64_gflops.restype = ctypes.c_double
+    lib.mpcgpu_measure_fp64_gflops.argtypes = [ctypes.c_int]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise MpcGpuError(f"{what} failed ({rc}): {load_library().mpcgpu_strerror(rc).decode()}")
+
+
+def infos_to_dicts(info):
+    return [dict(pobj=i.pobj, res_eq=i.res_eq, res_stat_qp=i.res_stat_qp, res_comp_qp=i.res_comp_qp, exit_code=i.exit_code,
+                 qp_status=i.qp_status, sqp_iter=i.sqp_iter, qp_iter=i.qp_iter) for i in info]
+
+
+INFO_DTYPE = np.dtype([("pobj", "f8"), ("res_eq", "f8"), ("res_stat_qp", "f8"), ("res_comp_qp", "f8"), ("exit_code", "i4"),
+                       ("qp_status", "i4"), ("sqp_iter", "i4"), ("qp_iter", "i4")])
+assert INFO_DTYPE.itemsize == ctypes.sizeof(SolveInfo)
+
+
+class BatchSolver:
+    """P simultaneous `Solver::solve()` calls on one GPU (mpcgpu_create / mpcgpu_solve_*)."""
+
+    def __init__(self, spec: ProblemSpec, max_batch: int, device: int = 0):
+        self.lib = load_library()
+        self.spec = spec
+        self.desc = spec.desc()
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        if not self.lib.mpcgpu_problem_supported(ctypes.byref(self.desc)):
+            raise MpcGpuError(f"problem '{spec.name}' has no compiled kernel specialisation (csrc/registry.cuh)")
+        h = ctypes.c_void_p()
+        _check(self.lib.mpcgpu_create(ctypes.byref(self.desc), self.device, self.max_batch, ctypes.byref(h)), "mpcgpu_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mpcgpu_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host-buffer path: what MPCPlanner::Solver::solve() / GuidanceConstraints::optimize use ----
+    def solve(self, xinit, x0, params):
+        """Arrays [P, ...] in the reference's flat layouts.  Returns (xtraj, utraj, infos, best)."""
+        s = self.spec
+        xinit = np.ascontiguousarray(xinit, float).reshape(-1, s.nx)
+        P = xinit.shape[0]
+        x0 = np.ascontiguousarray(x0, float).reshape(P, s.nz * (s.N + 1))
+        params = np.ascontiguousarray(params, float).reshape(P, s.npar * s.N)
+        xtraj, utraj = np.empty((P, s.N + 1, s.nx)), np.empty((P, s.N, s.nu))
+        info = (SolveInfo * P)()
+        best = ctypes.c_int(-1)
+        _check(self.lib.mpcgpu_solve_host(self.handle, P, _p(xinit), _p(x0), _p(params), _p(xtraj), _p(utraj), info,
+                                          ctypes.byref(best)), "mpcgpu_solve_host")
+        return xtraj, utraj, infos_to_dicts(info), int(best.value)
+
+    # ---- device-buffer path (raw pointers, e.g. torch tensors' data_ptr()) ----
+    def solve_device(self, P, d_xinit, d_x0, d_params, d_xtraj, d_utraj, d_info, d_best=None, stream=None):
+        _check(self.lib.mpcgpu_solve_device(self.handle, int(P), d_xinit, d_x0, d_params, d_xtraj, d_utraj, d_info, d_best, stream),
+               "mpcgpu_solve_device")
+
+    def eval_stage(self, z, p, lam=None, pi=None):
+        d = self.desc
+        nz, nx, nh = d.nx + d.nu, d.nx, d.nh
+        z = np.ascontiguousarray(z, float).reshape(-1, nz)
+        M = z.shape[0]
+        p = np.ascontiguousarray(p, float).reshape(M, d.npar)
+        lam = np.zeros((M, max(nh, 1))) if lam is None else np.ascontiguousarray(lam, float).reshape(M, -1)
+        pi = np.zeros((M, nx)) if pi is None else np.ascontiguousarray(pi, float).reshape(M, nx)
+        out = dict(cost=np.zeros(M), cost_grad=np.zeros((M, nz)), cost_hess=np.zeros((M, nz, nz)), h=np.zeros((M, max(nh, 1))),
+                   h_jac=np.zeros((M, max(nh, 1), nz)), h_hess=np.zeros((M, nz, nz)), xnext=np.zeros((M, nx)),
+                   AB=np.zeros((M, nx, nz)), dyn_hess=np.zeros((M, nz, nz)))
+        _check(self.lib.mpcgpu_eval_stage(self.handle, M, _p(z), _p(p), _p(lam), _p(pi), _p(out["cost"]), _p(out["cost_grad"]),
+                                          _p(out["cost_hess"]), _p(out["h"]), _p(out["h_jac"]), _p(out["h_hess"]), _p(out["xnext"]),
+                                          _p(out["AB"]), _p(out["dyn_hess"])), "mpcgpu_eval_stage")
+        out["h"], out["h_jac"] = out["h"][:, :nh], out["h_jac"][:, :nh]
+        return out
+
+    def set_timing(self, enabled=True):
+        _check(self.lib.mpcgpu_set_timing(self.handle, int(enabled)), "mpcgpu_set_timing")
+
+    def kernel_ms(self):
+        n = ctypes.c_int(0)
+        ms = self.lib.mpcgpu_kernel_ms(self.handle, ctypes.byref(n))
+        return float(ms), int(n.value)
+
+    @property
+    def launches(self):
+        return int(self.lib.mpcgpu_launch_count(self.handle))

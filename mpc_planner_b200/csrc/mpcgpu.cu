@@ -1,0 +1,432 @@
+// mpcgpu.cu -- CUDA kernels and the C ABI (include/mpcgpu.h) of the B200 batched SQP backend.
+//
+// Launch geometry: one warp (= one 32-thread CTA) per solve, the whole NLP/QP of that solve in
+// shared memory (SL<CFG>::TOTAL doubles, ~54 KB for the T-MPC stack => 4 CTAs per SM).
+// Kernels per batch:  transpose_params (reference stage-major parameters -> lane-major so that
+// lane = stage loads coalesce)  ->  sqp_kernel  ->  select_best (FindBestPlanner argmin).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "registry.cuh"
+
+using namespace mpcgpu;
+
+namespace {
+
+enum {
+    MPCGPU_OK = 0,
+    MPCGPU_ERR_ARG = -1,
+    MPCGPU_ERR_UNSUPPORTED = -2,
+    MPCGPU_ERR_CUDA = -3,
+    MPCGPU_ERR_NO_DEVICE = -4,
+    MPCGPU_ERR_BATCH = -5,
+    MPCGPU_ERR_ALLOC = -6
+};
+
+thread_local char g_last_cuda_error[256] = "";
+
+#define CUDA_TRY(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", #expr, cudaGetErrorString(e__)); \
+            return MPCGPU_ERR_CUDA;                                                                           \
+        }                                                                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+// params[P][N][npar] (AcadosParameters::all_parameters, stage-major) -> pt[P][npar][32]
+__global__ void transpose_params_kernel(const double *__restrict__ params, double *__restrict__ pt, int P, int N, int npar) {
+    const long long total = (long long)P * N * npar;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % npar);
+        const long long pk = idx / npar;
+        const int k = (int)(pk % N);
+        const long long p = pk / N;
+        pt[(p * npar + i) * 32 + k] = params[idx];
+    }
+}
+
+template <class CFG>
+__global__ void __launch_bounds__(32) sqp_kernel(Layout L, int P, const double *__restrict__ xinit, const double *__restrict__ x0,
+                                                 const double *__restrict__ pt, double *__restrict__ xtraj,
+                                                 double *__restrict__ utraj, mpcgpu_info *__restrict__ info) {
+    extern __shared__ double sm[];
+    const int p = blockIdx.x;
+    if (p >= P) return;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU;
+    sqp_solve_warp<CFG>(L, sm, xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt + (size_t)p * L.npar * 32,
+                        xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p, nullptr);
+}
+
+// FindBestPlanner (mpc_planner_modules/src/guidance_constraints.cpp:416-434): index of the
+// successful solve with the smallest objective, -1 if none.  One CTA.
+__global__ void select_best_kernel(const mpcgpu_info *__restrict__ info, int P, int *__restrict__ best) {
+    __shared__ double s_obj[256];
+    __shared__ int s_idx[256];
+    double bo = 1e10;  // the reference's sentinel (guidance_constraints.cpp:419)
+    int bi = -1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double o = info[i].pobj;
+        if (info[i].exit_code == 1 && (o < bo)) {
+            bo = o;
+            bi = i;
+        }
+    }
+    s_obj[threadIdx.x] = bo;
+    s_idx[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double o = s_obj[threadIdx.x + s];
+            const int j = s_idx[threadIdx.x + s];
+            // strict '<' with lowest index winning ties, as the serial loop of the reference does
+            if (j >= 0 && (o < s_obj[threadIdx.x] || (o == s_obj[threadIdx.x] && (s_idx[threadIdx.x] < 0 || j < s_idx[threadIdx.x])))) {
+                s_obj[threadIdx.x] = o;
+                s_idx[threadIdx.x] = j;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *best = s_idx[0];
+}
+
+template <class CFG>
+__global__ void eval_stage_kernel(Layout L, int M, const double *z, const double *p, const double *lam, const double *pi,
+                                  double *cost, double *cost_grad, double *cost_hess, double *hval, double *h_jac,
+                                  double *h_hess, double *xnext, double *AB, double *dyn_hess) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    constexpr int nz = CFG::NZ, nx = CFG::NX, nh = CFG::NH;
+    eval_stage_sample<CFG>(L, z + (size_t)m * nz, p + (size_t)m * L.npar, lam ? lam + (size_t)m * nh : nullptr,
+                           pi ? pi + (size_t)m * nx : nullptr, cost ? cost + m : nullptr,
+                           cost_grad ? cost_grad + (size_t)m * nz : nullptr, cost_hess ? cost_hess + (size_t)m * nz * nz : nullptr,
+                           hval ? hval + (size_t)m * nh : nullptr, h_jac ? h_jac + (size_t)m * nh * nz : nullptr,
+                           h_hess ? h_hess + (size_t)m * nz * nz : nullptr, xnext ? xnext + (size_t)m * nx : nullptr,
+                           AB ? AB + (size_t)m * nx * nz : nullptr, dyn_hess ? dyn_hess + (size_t)m * nz * nz : nullptr);
+}
+
+// dependent-free FP64 FMA chains: 8 independent accumulators per thread
+__global__ void fp64_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------------------------
+// solver object
+// ---------------------------------------------------------------------------------------------
+struct KernelTable {
+    const char *name;
+    bool (*matches)(const mpcgpu_problem_desc &);
+    int smem_bytes;
+    cudaError_t (*prepare)(int smem_bytes);
+    void (*launch_sqp)(const Layout &, int P, const double *, const double *, const double *, double *, double *, mpcgpu_info *,
+                       int smem, cudaStream_t);
+    void (*launch_eval)(const Layout &, int M, const double *, const double *, const double *, const double *, double *, double *,
+                        double *, double *, double *, double *, double *, double *, double *, cudaStream_t);
+};
+
+template <class CFG>
+cudaError_t prepare_cfg(int smem_bytes) {
+    return cudaFuncSetAttribute(sqp_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+template <class CFG>
+void launch_sqp_cfg(const Layout &L, int P, const double *xinit, const double *x0, const double *pt, double *xtraj, double *utraj,
+                    mpcgpu_info *info, int smem, cudaStream_t s) {
+    sqp_kernel<CFG><<<P, 32, smem, s>>>(L, P, xinit, x0, pt, xtraj, utraj, info);
+}
+template <class CFG>
+void launch_eval_cfg(const Layout &L, int M, const double *z, const double *p, const double *lam, const double *pi, double *cost,
+                     double *cost_grad, double *cost_hess, double *hval, double *h_jac, double *h_hess, double *xnext, double *AB,
+                     double *dyn_hess, cudaStream_t s) {
+    eval_stage_kernel<CFG><<<(M + 63) / 64, 64, 0, s>>>(L, M, z, p, lam, pi, cost, cost_grad, cost_hess, hval, h_jac, h_hess, xnext,
+                                                       AB, dyn_hess);
+}
+
+#define X(C) {#C, &config_matches<C>, (int)(SL<C>::TOTAL * sizeof(double)), &prepare_cfg<C>, &launch_sqp_cfg<C>, &launch_eval_cfg<C>},
+const KernelTable g_table[] = {MPCGPU_CONFIG_LIST(X)};
+#undef X
+const int g_table_size = sizeof(g_table) / sizeof(g_table[0]);
+
+const KernelTable *find_kernel(const mpcgpu_problem_desc &d) {
+    for (int i = 0; i < g_table_size; i++)
+        if (g_table[i].matches(d)) return &g_table[i];
+    return nullptr;
+}
+
+}  // namespace
+
+struct mpcgpu_solver {
+    mpcgpu_problem_desc desc;
+    Layout layout;
+    const KernelTable *kt;
+    int device, max_batch;
+    cudaStream_t stream;  // owned stream for the host path
+    // device buffers (host path)
+    double *d_xinit, *d_x0, *d_params, *d_pt, *d_xtraj, *d_utraj;
+    mpcgpu_info *d_info;
+    int *d_best;
+    long long launches;
+    int timing;
+    cudaEvent_t ev0, ev1;
+    double ms_acc;
+    int ms_n;
+    // sizes per solve
+    size_t n_xinit, n_x0, n_params, n_xtraj, n_utraj;
+};
+
+extern "C" {
+
+const char *mpcgpu_version(void) { return "mpcgpu 0.1 (sm_100a)"; }
+
+const char *mpcgpu_strerror(int code) {
+    switch (code) {
+    case MPCGPU_OK: return "ok";
+    case MPCGPU_ERR_ARG: return "invalid argument";
+    case MPCGPU_ERR_UNSUPPORTED: return "no kernel specialisation compiled for this problem (see csrc/registry.cuh)";
+    case MPCGPU_ERR_CUDA: return g_last_cuda_error[0] ? g_last_cuda_error : "CUDA error";
+    case MPCGPU_ERR_NO_DEVICE: return "no CUDA device available: the CUDA backend has no CPU fallback";
+    case MPCGPU_ERR_BATCH: return "batch larger than max_batch of the handle";
+    case MPCGPU_ERR_ALLOC: return "allocation failed";
+    }
+    return "unknown error";
+}
+
+int mpcgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int mpcgpu_problem_supported(const mpcgpu_problem_desc *desc) { return (desc && find_kernel(*desc)) ? 1 : 0; }
+
+int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mpcgpu_handle *out) {
+    if (!desc || !out || max_batch <= 0) return MPCGPU_ERR_ARG;
+    *out = nullptr;
+    const KernelTable *kt = find_kernel(*desc);
+    if (!kt) return MPCGPU_ERR_UNSUPPORTED;
+    if (mpcgpu_device_count() <= device || device < 0) return MPCGPU_ERR_NO_DEVICE;
+    CUDA_TRY(cudaSetDevice(device));
+    mpcgpu_solver *h = new (std::nothrow) mpcgpu_solver();
+    if (!h) return MPCGPU_ERR_ALLOC;
+    memset(h, 0, sizeof(*h));
+    h->desc = *desc;
+    h->layout = make_layout(*desc);
+    h->kt = kt;
+    h->device = device;
+    h->max_batch = max_batch;
+    const int N = desc->N, nx = desc->nx, nu = desc->nu, nz = nx + nu;
+    h->n_xinit = nx;
+    h->n_x0 = (size_t)nz * (N + 1);
+    h->n_params = (size_t)desc->npar * N;
+    h->n_xtraj = (size_t)nx * (N + 1);
+    h->n_utraj = (size_t)nu * N;
+    cudaError_t e = kt->prepare(kt->smem_bytes);
+    if (e != cudaSuccess) {
+        snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cudaFuncSetAttribute(smem=%d): %s", kt->smem_bytes, cudaGetErrorString(e));
+        delete h;
+        return MPCGPU_ERR_CUDA;
+    }
+    const size_t B = (size_t)max_batch;
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_xinit, B * h->n_xinit * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_x0, B * h->n_x0 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_params, B * h->n_params * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_pt, B * (size_t)desc->npar * 32 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_xtraj, B * h->n_xtraj * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_utraj, B * h->n_utraj * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_info, B * sizeof(mpcgpu_info)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_best, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->d_pt, 0, B * (size_t)desc->npar * 32 * sizeof(double)) == cudaSuccess;
+    if (!ok) {
+        snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        mpcgpu_destroy(h);
+        return MPCGPU_ERR_CUDA;
+    }
+    *out = h;
+    return MPCGPU_OK;
+}
+
+int mpcgpu_destroy(mpcgpu_handle h) {
+    if (!h) return MPCGPU_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_xinit);
+    cudaFree(h->d_x0);
+    cudaFree(h->d_params);
+    cudaFree(h->d_pt);
+    cudaFree(h->d_xtraj);
+    cudaFree(h->d_utraj);
+    cudaFree(h->d_info);
+    cudaFree(h->d_best);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MPCGPU_OK;
+}
+
+int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const double *d_x0, const double *d_params,
+                        double *d_xtraj, double *d_utraj, mpcgpu_info *d_info, int *d_best, void *stream) {
+    if (!h || P <= 0 || !d_xinit || !d_x0 || !d_params || !d_xtraj || !d_utraj || !d_info) return MPCGPU_ERR_ARG;
+    if (P > h->max_batch) return MPCGPU_ERR_BATCH;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = h->desc.N, npar = h->desc.npar;
+    const long long total = (long long)P * N * npar;
+    int tb = (int)((total + 255) / 256);
+    if (tb > 148 * 16) tb = 148 * 16;
+    transpose_params_kernel<<<tb, 256, 0, s>>>(d_params, h->d_pt, P, N, npar);
+    if (h->timing) cudaEventRecord(h->ev0, s);
+    h->kt->launch_sqp(h->layout, P, d_xinit, d_x0, h->d_pt, d_xtraj, d_utraj, d_info, h->kt->smem_bytes, s);
+    if (h->timing) cudaEventRecord(h->ev1, s);
+    h->launches += 2;
+    if (d_best) {
+        select_best_kernel<<<1, 256, 0, s>>>(d_info, P, d_best);
+        h->launches += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (h->timing) {
+        CUDA_TRY(cudaEventSynchronize(h->ev1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->ms_acc += ms;
+        h->ms_n += 1;
+    }
+    return MPCGPU_OK;
+}
+
+int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double *x0, const double *params, double *xtraj,
+                      double *utraj, mpcgpu_info *info, int *best) {
+    if (!h || P <= 0 || !xinit || !x0 || !params || !xtraj || !utraj || !info) return MPCGPU_ERR_ARG;
+    if (P > h->max_batch) return MPCGPU_ERR_BATCH;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t B = (size_t)P;
+    CUDA_TRY(cudaMemcpyAsync(h->d_xinit, xinit, B * h->n_xinit * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_x0, x0, B * h->n_x0 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_params, params, B * h->n_params * sizeof(double), cudaMemcpyHostToDevice, s));
+    int rc = mpcgpu_solve_device(h, P, h->d_xinit, h->d_x0, h->d_params, h->d_xtraj, h->d_utraj, h->d_info, h->d_best, (void *)s);
+    if (rc != MPCGPU_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(xtraj, h->d_xtraj, B * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(utraj, h->d_utraj, B * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(info, h->d_info, B * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, s));
+    int hbest = -1;
+    CUDA_TRY(cudaMemcpyAsync(&hbest, h->d_best, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (best) *best = hbest;
+    return MPCGPU_OK;
+}
+
+int mpcgpu_host_alloc(void **ptr, unsigned long long bytes) {
+    if (!ptr) return MPCGPU_ERR_ARG;
+    CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return MPCGPU_OK;
+}
+int mpcgpu_host_free(void *ptr) {
+    CUDA_TRY(cudaFreeHost(ptr));
+    return MPCGPU_OK;
+}
+
+long long mpcgpu_launch_count(mpcgpu_handle h) { return h ? h->launches : 0; }
+
+int mpcgpu_set_timing(mpcgpu_handle h, int enabled) {
+    if (!h) return MPCGPU_ERR_ARG;
+    h->timing = enabled;
+    h->ms_acc = 0.0;
+    h->ms_n = 0;
+    return MPCGPU_OK;
+}
+double mpcgpu_kernel_ms(mpcgpu_handle h, int *n_launches) {
+    if (!h) return 0.0;
+    const double v = h->ms_n ? h->ms_acc / h->ms_n : 0.0;
+    if (n_launches) *n_launches = h->ms_n;
+    h->ms_acc = 0.0;
+    h->ms_n = 0;
+    return v;
+}
+
+int mpcgpu_eval_stage(mpcgpu_handle h, int M, const double *z, const double *p, const double *lam, const double *pi, double *cost,
+                      double *cost_grad, double *cost_hess, double *hval, double *h_jac, double *h_hess, double *xnext, double *AB,
+                      double *dyn_hess) {
+    if (!h || M <= 0 || !z || !p) return MPCGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int nz = h->desc.nx + h->desc.nu, nx = h->desc.nx, nh = h->desc.nh, npar = h->desc.npar;
+    struct Buf {
+        double *d;
+        double *host;
+        size_t n;
+    };
+    const double *ins[4] = {z, p, lam, pi};
+    const size_t in_n[4] = {(size_t)M * nz, (size_t)M * npar, (size_t)M * nh, (size_t)M * nx};
+    double *d_in[4] = {nullptr, nullptr, nullptr, nullptr};
+    Buf outs[9] = {{nullptr, cost, (size_t)M},          {nullptr, cost_grad, (size_t)M * nz}, {nullptr, cost_hess, (size_t)M * nz * nz},
+                   {nullptr, hval, (size_t)M * nh},     {nullptr, h_jac, (size_t)M * nh * nz}, {nullptr, h_hess, (size_t)M * nz * nz},
+                   {nullptr, xnext, (size_t)M * nx},    {nullptr, AB, (size_t)M * nx * nz},   {nullptr, dyn_hess, (size_t)M * nz * nz}};
+    int rc = MPCGPU_OK;
+    for (int i = 0; i < 4 && rc == MPCGPU_OK; i++)
+        if (ins[i] && in_n[i]) {
+            if (cudaMalloc(&d_in[i], in_n[i] * sizeof(double)) != cudaSuccess ||
+                cudaMemcpy(d_in[i], ins[i], in_n[i] * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+                rc = MPCGPU_ERR_CUDA;
+        }
+    for (int i = 0; i < 9 && rc == MPCGPU_OK; i++)
+        if (outs[i].host && outs[i].n)
+            if (cudaMalloc(&outs[i].d, outs[i].n * sizeof(double)) != cudaSuccess) rc = MPCGPU_ERR_CUDA;
+    if (rc == MPCGPU_OK) {
+        h->kt->launch_eval(h->layout, M, d_in[0], d_in[1], d_in[2], d_in[3], outs[0].d, outs[1].d, outs[2].d, outs[3].d, outs[4].d,
+                           outs[5].d, outs[6].d, outs[7].d, outs[8].d, 0);
+        h->launches += 1;
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = MPCGPU_ERR_CUDA;
+    }
+    for (int i = 0; i < 9 && rc == MPCGPU_OK; i++)
+        if (outs[i].d && cudaMemcpy(outs[i].host, outs[i].d, outs[i].n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = MPCGPU_ERR_CUDA;
+    if (rc != MPCGPU_OK) snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "eval_stage: %s", cudaGetErrorString(cudaGetLastError()));
+    for (int i = 0; i < 4; i++) cudaFree(d_in[i]);
+    for (int i = 0; i < 9; i++) cudaFree(outs[i].d);
+    return rc;
+}
+
+double mpcgpu_measure_fp64_gflops(int device) {
+    if (mpcgpu_device_count() <= device || device < 0) return -1.0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double *d_out = nullptr;
+    if (cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    fp64_peak_kernel<<<blocks, threads>>>(d_out, 1024);  // warm up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(d_out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        const double gf = flops / (ms * 1e-3) * 1e-9;
+        if (gf > best) best = gf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return best;
+}
+
+}  // extern "C"
