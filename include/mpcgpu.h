@@ -127,9 +127,9 @@ int mpcgpu_destroy(mpcgpu_handle h);
 /* Host-buffer path (what Solver::solve() uses): upload -> solve -> download, synchronous.
  *   xinit[P*nx], x0[P*(nu+nx)*(N+1)], params[P*npar*N]  -> xtraj[P*nx*(N+1)], utraj[P*nu*N], info[P]
  * Replaces initializeOneIteration + n_sqp x solveOneIteration + completeOneIteration
- * (acados_solver_interface.cpp:86-204) for P solvers at once.  best (may be NULL) receives the
- * index of the successful solve with the smallest pobj (FindBestPlanner,
- * mpc_planner_modules/src/guidance_constraints.cpp:416-434), or -1 if none succeeded. */
+ * (acados_solver_interface.cpp:86-204) for P solvers at once.  best (may be NULL) receives, per
+ * selection group (see mpcgpu_set_group), the index of the successful solve with the smallest pobj
+ * (FindBestPlanner, mpc_planner_modules/src/guidance_constraints.cpp:416-434), or -1 if none. */
 int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double *x0,
                       const double *params, double *xtraj, double *utraj, mpcgpu_info *info,
                       int *best);
@@ -139,6 +139,11 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
 int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const double *d_x0,
                         const double *d_params, double *d_xtraj, double *d_utraj,
                         mpcgpu_info *d_info, int *d_best, void *stream);
+
+/* Selection groups: consecutive blocks of `group` solves are the guesses of one control step;
+ * `best` / `d_best` then receive ceil(P/group) entries, each the within-group index of the winner
+ * (or -1).  group = 0 (default) treats the whole batch as one group. */
+int mpcgpu_set_group(mpcgpu_handle h, int group);
 
 /* Pinned host staging buffers for the host path (optional; plain malloc'd memory also works). */
 int mpcgpu_host_alloc(void **ptr, unsigned long long bytes);

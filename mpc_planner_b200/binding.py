@@ -20,7 +20,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 # every symbol include/mpcgpu.h declares
 EXPORTED_SYMBOLS = [
     "mpcgpu_version", "mpcgpu_strerror", "mpcgpu_device_count", "mpcgpu_problem_supported", "mpcgpu_create", "mpcgpu_destroy",
-    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
+    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_set_group", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
     "mpcgpu_set_timing", "mpcgpu_kernel_ms", "mpcgpu_eval_stage", "mpcgpu_measure_fp64_gflops",
 ]
 
@@ -46,6 +46,7 @@ def load_library():
     lib.mpcgpu_destroy.argtypes = [ctypes.c_void_p]
     lib.mpcgpu_solve_host.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, ctypes.POINTER(SolveInfo), _ip]
     lib.mpcgpu_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 8
+    lib.mpcgpu_set_group.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.mpcgpu_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_ulonglong]
     lib.mpcgpu_host_free.argtypes = [ctypes.c_void_p]
     lib.mpcgpu_launch_count.restype = ctypes.c_longlong
@@ -93,6 +94,12 @@ class BatchSolver:
         h = ctypes.c_void_p()
         _check(self.lib.mpcgpu_create(ctypes.byref(self.desc), self.device, self.max_batch, ctypes.byref(h)), "mpcgpu_create")
         self.handle = h
+        self.group = 0
+
+    def set_group(self, group: int):
+        """Guesses per control step: `best` becomes one winner index per group of consecutive solves."""
+        _check(self.lib.mpcgpu_set_group(self.handle, int(group)), "mpcgpu_set_group")
+        self.group = int(group)
 
     def close(self):
         if getattr(self, "handle", None):
@@ -115,10 +122,11 @@ class BatchSolver:
         params = np.ascontiguousarray(params, float).reshape(P, s.npar * s.N)
         xtraj, utraj = np.empty((P, s.N + 1, s.nx)), np.empty((P, s.N, s.nu))
         info = (SolveInfo * P)()
-        best = ctypes.c_int(-1)
+        group = self.group if self.group > 0 else P
+        best = np.full((P + group - 1) // group, -1, dtype=np.int32)
         _check(self.lib.mpcgpu_solve_host(self.handle, P, _p(xinit), _p(x0), _p(params), _p(xtraj), _p(utraj), info,
-                                          ctypes.byref(best)), "mpcgpu_solve_host")
-        return xtraj, utraj, infos_to_dicts(info), int(best.value)
+                                          best.ctypes.data_as(_ip)), "mpcgpu_solve_host")
+        return xtraj, utraj, infos_to_dicts(info), (int(best[0]) if self.group == 0 else best)
 
     # ---- device-buffer path (raw pointers, e.g. torch tensors' data_ptr()) ----
     def solve_device(self, P, d_xinit, d_x0, d_params, d_xtraj, d_utraj, d_info, d_best=None, stream=None):

@@ -65,36 +65,32 @@ __global__ void __launch_bounds__(32) sqp_kernel(Layout L, int P, const double *
                         xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p, nullptr);
 }
 
-// FindBestPlanner (mpc_planner_modules/src/guidance_constraints.cpp:416-434): index of the
-// successful solve with the smallest objective, -1 if none.  One CTA.
-__global__ void select_best_kernel(const mpcgpu_info *__restrict__ info, int P, int *__restrict__ best) {
-    __shared__ double s_obj[256];
-    __shared__ int s_idx[256];
+// FindBestPlanner (mpc_planner_modules/src/guidance_constraints.cpp:416-434): per group of `group`
+// consecutive solves (the guesses of one control step), index of the successful solve with the
+// smallest objective, -1 if none.  One warp per group; ties resolve to the lowest index as in the
+// reference's serial loop.
+__global__ void select_best_kernel(const mpcgpu_info *__restrict__ info, int P, int group, int n_groups, int *__restrict__ best) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_groups) return;
+    const int base = warp * group, end = min(base + group, P);
     double bo = 1e10;  // the reference's sentinel (guidance_constraints.cpp:419)
-    int bi = -1;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    int bi = 0x7fffffff;
+    for (int i = base + lane; i < end; i += 32) {
         const double o = info[i].pobj;
         if (info[i].exit_code == 1 && (o < bo)) {
             bo = o;
             bi = i;
         }
     }
-    s_obj[threadIdx.x] = bo;
-    s_idx[threadIdx.x] = bi;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            const double o = s_obj[threadIdx.x + s];
-            const int j = s_idx[threadIdx.x + s];
-            // strict '<' with lowest index winning ties, as the serial loop of the reference does
-            if (j >= 0 && (o < s_obj[threadIdx.x] || (o == s_obj[threadIdx.x] && (s_idx[threadIdx.x] < 0 || j < s_idx[threadIdx.x])))) {
-                s_obj[threadIdx.x] = o;
-                s_idx[threadIdx.x] = j;
-            }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, bo, off);
+        const int j = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (o < bo || (o == bo && j < bi)) {
+            bo = o;
+            bi = j;
         }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) *best = s_idx[0];
+    if (lane == 0) best[warp] = (bi == 0x7fffffff) ? -1 : bi - base;
 }
 
 template <class CFG>
@@ -178,6 +174,7 @@ struct mpcgpu_solver {
     mpcgpu_info *d_info;
     int *d_best;
     long long launches;
+    int group;  // solves per selection group (0 = the whole batch)
     int timing;
     cudaEvent_t ev0, ev1;
     double ms_acc;
@@ -248,7 +245,7 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     ok = ok && cudaMalloc(&h->d_xtraj, B * h->n_xtraj * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_utraj, B * h->n_utraj * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_info, B * sizeof(mpcgpu_info)) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_best, sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_best, B * sizeof(int)) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
     if (ok) ok = cudaMemset(h->d_pt, 0, B * (size_t)desc->npar * 32 * sizeof(double)) == cudaSuccess;
     if (!ok) {
@@ -293,7 +290,8 @@ int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const dou
     if (h->timing) cudaEventRecord(h->ev1, s);
     h->launches += 2;
     if (d_best) {
-        select_best_kernel<<<1, 256, 0, s>>>(d_info, P, d_best);
+        const int group = (h->group > 0) ? h->group : P, n_groups = (P + group - 1) / group;
+        select_best_kernel<<<(n_groups + 3) / 4, 128, 0, s>>>(d_info, P, group, n_groups, d_best);
         h->launches += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -322,10 +320,9 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
     CUDA_TRY(cudaMemcpyAsync(xtraj, h->d_xtraj, B * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(utraj, h->d_utraj, B * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(info, h->d_info, B * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, s));
-    int hbest = -1;
-    CUDA_TRY(cudaMemcpyAsync(&hbest, h->d_best, sizeof(int), cudaMemcpyDeviceToHost, s));
+    const int group = (h->group > 0) ? h->group : P, n_groups = (P + group - 1) / group;
+    if (best) CUDA_TRY(cudaMemcpyAsync(best, h->d_best, (size_t)n_groups * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (best) *best = hbest;
     return MPCGPU_OK;
 }
 
@@ -336,6 +333,12 @@ int mpcgpu_host_alloc(void **ptr, unsigned long long bytes) {
 }
 int mpcgpu_host_free(void *ptr) {
     CUDA_TRY(cudaFreeHost(ptr));
+    return MPCGPU_OK;
+}
+
+int mpcgpu_set_group(mpcgpu_handle h, int group) {
+    if (!h || group < 0) return MPCGPU_ERR_ARG;
+    h->group = group;
     return MPCGPU_OK;
 }
 

@@ -671,7 +671,9 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
                 if (lane == 0) {
                     const double mu_aff = red_sum32(W + S::W_RED) / nc;
                     const double ratio = (mu > 0.0) ? mu_aff / mu : 0.0;
-                    W[S::W_SC + SC_SIGMU] = ratio * ratio * ratio * mu;
+                    // Mehrotra centering, floored at a fraction of the complementarity tolerance: driving mu
+                    // far below qp_tol only makes lam/t huge and buries the stationarity residual in round-off
+                    W[S::W_SC + SC_SIGMU] = fmax(ratio * ratio * ratio * mu, 0.1 * L.qp_tol);
                 }
                 MPC_LANES_END
             }

@@ -1,0 +1,77 @@
+"""The kernel SOURCE (mpc_planner_b200/csrc/*.cuh), compiled for the host as a sequential warp
+emulation (tests/emu), against the CPU oracle.  This exercises the hand-derived derivatives and
+the warp-phased SQP / IPM / Riccati logic on the CPU; the GPU parity tests (-m gpu) run the same
+source through nvcc and the C ABI."""
+import numpy as np
+import pytest
+
+from mpc_planner_b200 import problem as pb
+from mpc_planner_b200 import scenes
+from oracle import oracle
+from tests.emu import emu
+
+SPECS = {
+    "cfg1": pb.config_basic(),
+    "cfg2": pb.config_tmpc(),
+    "cfg2_gaussian": pb.config_tmpc(gaussian=True),
+    "cfg3": pb.config_tmpc_decomp(),
+    "cfg4": pb.config_safe_horizon(),
+}
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_hand_derived_derivatives_match_oracle_ad(golden, name):
+    spec, g = SPECS[name], golden[name]
+    d = spec.desc()
+    rng = np.random.default_rng(0)
+    for s in g["samples"]:
+        z, p = np.array(s["z"]), np.array(s["p"])
+        lam, pi = rng.uniform(0, 1, spec.nh), rng.uniform(-1, 1, spec.nx)
+        o = oracle.eval_stage(d, z, p, lam, pi)
+        e = emu.eval_stage(d, z, p, lam, pi)
+        assert e["cost"][0] == pytest.approx(s["cost"], rel=1e-12, abs=1e-12)  # the reference's own value
+        np.testing.assert_allclose(e["h"][0], s["h"], rtol=1e-12, atol=1e-12)
+        for key in ("cost_grad", "cost_hess", "h_jac", "h_hess", "xnext", "AB", "dyn_hess"):
+            ref = np.asarray(o[key])
+            np.testing.assert_allclose(e[key][0], ref, rtol=1e-10, atol=1e-11 * (1 + np.abs(ref).max()), err_msg=key)
+
+
+@pytest.mark.parametrize("name,S,P", [("cfg2", 3, 8), ("cfg1", 6, 1), ("cfg2_gaussian", 2, 4)])
+def test_emulated_kernel_solves_match_oracle(name, S, P):
+    spec = SPECS[name]
+    b = scenes.make_scene_batch(spec, S, P, seed=31)
+    xt, ut, info = oracle.solve_batch(spec, b["xinit"], b["x0"], b["params"])
+    ext, eut, einfo = emu.solve_batch(spec, b["xinit"], b["x0"], b["params"])
+    n_ok = 0
+    for i in range(S * P):
+        assert einfo[i]["exit_code"] == info[i]["exit_code"], (i, einfo[i], info[i])
+        assert einfo[i]["qp_status"] == info[i]["qp_status"]
+        if info[i]["exit_code"] == 1:
+            n_ok += 1
+            np.testing.assert_allclose(ext[i], xt[i], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(eut[i], ut[i], rtol=1e-6, atol=1e-6)
+            assert einfo[i]["pobj"] == pytest.approx(info[i]["pobj"], rel=1e-6, abs=1e-6)
+    assert n_ok >= max(1, S * P // 3)
+
+
+def test_scene_generator_invariants():
+    spec = pb.config_tmpc()
+    b = scenes.make_scene_batch(spec, 2, 8, seed=4)
+    pm = spec.parameter_map()
+    N, npar, nz, nu = spec.N, spec.npar, spec.nz, spec.nu
+    par = b["params"].reshape(16, N, npar)
+    x0 = b["x0"].reshape(16, N + 1, nz)
+    # stage-0 dummies (ellipsoid_constraints.cpp:42-55, linearized_constraints.cpp:155-166)
+    np.testing.assert_allclose(par[:, 0, pm["ellipsoid_obst_0_x"]], b["xinit"][:, 0] + 50)
+    np.testing.assert_allclose(par[:, 0, pm["lin_constraint_0_a1"]], 1.0)
+    np.testing.assert_allclose(par[:, 0, pm["lin_constraint_0_b"]], b["xinit"][:, 0] + 100)
+    # guess 0 is the non-guided planner: dummy halfspaces at every stage
+    np.testing.assert_allclose(par[0, :, pm["lin_constraint_3_a2"]], 0.0)
+    # warm starts are dynamically consistent and start at xinit
+    np.testing.assert_allclose(x0[:, 0, nu:], b["xinit"])
+    # guided guesses satisfy their own topology halfspaces strictly
+    for i in range(1, 8):
+        for k in range(1, N):
+            for o in range(8):
+                a1, a2, bb = (par[i, k, pm[f"lin_constraint_{o}_{s}"]] for s in ("a1", "a2", "b"))
+                assert a1 * x0[i, k, nu] + a2 * x0[i, k, nu + 1] - bb < 0
