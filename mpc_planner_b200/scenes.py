@@ -287,6 +287,8 @@ def make_scene_batch(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int, seed: 
                 for k in range(1, N):
                     for o in range(min(n_obs, n_lin)):
                         dvec = obs_pos[o, k] - traj[k, [iz["x"], iz["y"]]]
+                        if np.linalg.norm(dvec) < 1e-9:  # projectToSafety would move the point; any direction will do
+                            dvec = np.array([1e-9, 0.0])
                         a = dvec / np.linalg.norm(dvec)
                         b = a @ obs_pos[o, k] - R
                         par[k, pm[f"lin_constraint_{o}_a1"]] = a[0]

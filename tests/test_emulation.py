@@ -69,9 +69,13 @@ def test_scene_generator_invariants():
     np.testing.assert_allclose(par[0, :, pm["lin_constraint_3_a2"]], 0.0)
     # warm starts are dynamically consistent and start at xinit
     np.testing.assert_allclose(x0[:, 0, nu:], b["xinit"])
-    # guided guesses satisfy their own topology halfspaces strictly
+    # topology halfspaces: unit normal towards the obstacle, plane 1e-3 + robot_radius from its centre
     for i in range(1, 8):
         for k in range(1, N):
             for o in range(8):
                 a1, a2, bb = (par[i, k, pm[f"lin_constraint_{o}_{s}"]] for s in ("a1", "a2", "b"))
-                assert a1 * x0[i, k, nu] + a2 * x0[i, k, nu + 1] - bb < 0
+                ox, oy = par[i, k, pm[f"ellipsoid_obst_{o}_x"]], par[i, k, pm[f"ellipsoid_obst_{o}_y"]]
+                assert a1 * a1 + a2 * a2 == pytest.approx(1.0)
+                assert bb == pytest.approx(a1 * ox + a2 * oy - (1e-3 + scenes.ROBOT_RADIUS))
+                dist = np.hypot(ox - x0[i, k, nu], oy - x0[i, k, nu + 1])
+                assert a1 * x0[i, k, nu] + a2 * x0[i, k, nu + 1] - bb == pytest.approx(-dist + 1e-3 + scenes.ROBOT_RADIUS)
