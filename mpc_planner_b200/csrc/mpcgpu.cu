@@ -1,7 +1,7 @@
 // mpcgpu.cu -- CUDA kernels and the C ABI (include/mpcgpu.h) of the B200 batched SQP backend.
 //
-// Launch geometry: one warp (= one 32-thread CTA) per solve, the whole NLP/QP of that solve in
-// shared memory (SL<CFG>::TOTAL doubles, ~54 KB for the T-MPC stack => 4 CTAs per SM).
+// Launch geometry: one 128-thread CTA per solve, the whole NLP/QP of that solve in shared memory
+// (SL<CFG>::TOTAL doubles, ~70 KB for the T-MPC stack => 3 CTAs = 12 warps per SM).
 // Kernels per batch:  transpose_params (reference stage-major parameters -> lane-major so that
 // lane = stage loads coalesce)  ->  sqp_kernel  ->  select_best (FindBestPlanner argmin).
 #include <cuda_runtime.h>
@@ -54,14 +54,14 @@ __global__ void transpose_params_kernel(const double *__restrict__ params, doubl
 }
 
 template <class CFG>
-__global__ void __launch_bounds__(32) sqp_kernel(Layout L, int P, const double *__restrict__ xinit, const double *__restrict__ x0,
+__global__ void __launch_bounds__(MPC_NT) sqp_kernel(Layout L, int P, const double *__restrict__ xinit, const double *__restrict__ x0,
                                                  const double *__restrict__ pt, double *__restrict__ xtraj,
                                                  double *__restrict__ utraj, mpcgpu_info *__restrict__ info) {
     extern __shared__ double sm[];
     const int p = blockIdx.x;
     if (p >= P) return;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU;
-    sqp_solve_warp<CFG>(L, sm, xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt + (size_t)p * L.npar * 32,
+    sqp_solve_cta<CFG>(L, sm, xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt + (size_t)p * L.npar * 32,
                         xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p, nullptr);
 }
 
@@ -140,7 +140,7 @@ cudaError_t prepare_cfg(int smem_bytes) {
 template <class CFG>
 void launch_sqp_cfg(const Layout &L, int P, const double *xinit, const double *x0, const double *pt, double *xtraj, double *utraj,
                     mpcgpu_info *info, int smem, cudaStream_t s) {
-    sqp_kernel<CFG><<<P, 32, smem, s>>>(L, P, xinit, x0, pt, xtraj, utraj, info);
+    sqp_kernel<CFG><<<P, MPC_NT, smem, s>>>(L, P, xinit, x0, pt, xtraj, utraj, info);
 }
 template <class CFG>
 void launch_eval_cfg(const Layout &L, int M, const double *z, const double *p, const double *lam, const double *pi, double *cost,

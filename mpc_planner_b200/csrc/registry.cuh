@@ -107,12 +107,19 @@ MPC_HD void eval_stage_sample(const Layout &L, const double *z, const double *p,
         }
     }
     if (xnext || AB || dyn_hess) {
-        double xn[NX], BA[NX * NZ], Hp[NHP];
-        for (int i = 0; i < NHP; i++) Hp[i] = 0.0;
-        unicycle_step<CFG>(L, z, xn, BA, pi, (pi && dyn_hess) ? Hp : nullptr);
+        double xn[NX], BA[NX * NZ], Hd[7] = {0, 0, 0, 0, 0, 0, 0};
+        unicycle_step<CFG>(L, z, xn, BA, pi, (pi && dyn_hess) ? Hd : nullptr);
         if (xnext) for (int i = 0; i < NX; i++) xnext[i] = xn[i];
         if (AB) for (int i = 0; i < NX * NZ; i++) AB[i] = BA[i];
-        if (dyn_hess) for (int i = 0; i < NZ; i++) for (int j = 0; j < NZ; j++) dyn_hess[i * NZ + j] = Hp[trisym(i, j)];
+        if (dyn_hess) {
+            for (int i = 0; i < NZ * NZ; i++) dyn_hess[i] = 0.0;
+            const int ia[7] = {CFG::IPSI, CFG::IPSI, CFG::IW, CFG::IPSI, CFG::IPSI, CFG::IW, CFG::IW};
+            const int ib[7] = {CFG::IPSI, CFG::IW, CFG::IW, CFG::IV, CFG::IA, CFG::IV, CFG::IA};
+            for (int e = 0; e < 7; e++) {
+                dyn_hess[ia[e] * NZ + ib[e]] = Hd[e];
+                dyn_hess[ib[e] * NZ + ia[e]] = Hd[e];
+            }
+        }
     }
 }
 
