@@ -288,114 +288,150 @@ MPC_HD void assemble_stage(const Layout &L, double *st) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Riccati sweeps (CTA cooperative)
+// Riccati sweeps.  The recursion is a serial chain over the horizon whose per-stage blocks are
+// tiny (nx = 5..6, nu = 2); measured on B200, a cooperative version (threads = matrix entries,
+// __syncthreads between the steps of a stage) spends most of its time in barriers and index
+// arithmetic.  Here ONE thread runs the whole sweep out of registers with fully unrolled,
+// constant-offset shared-memory accesses, exploiting the structure of the unicycle family:
+// A = I + E with E non-zero only in the (psi, v) columns.
 // ---------------------------------------------------------------------------------------------
-// Backward factorisation: for k = N-1..0   M = H + Gamma-terms + [B A]' P+ [B A];
+template <class CFG>
+struct RicIdx {
+    static constexpr int NE = 2;  // columns of A that differ from the identity: psi, v
+    MPC_HD static constexpr int ecol(int c) { return c == 0 ? 2 : 3; }  // x-index of psi, v
+    MPC_HD static constexpr int eidx(int xi) { return xi == 2 ? 0 : (xi == 3 ? 1 : -1); }
+};
+
+// Backward factorisation: for k = N-1..0   M = H + barrier terms + [B A]' P+ [B A];
 //   Luu = chol(Muu);  Lxu = Mxu Luu^-T;  P = Mxx - Lxu Lxu';  PC(k+1) = P_{k+1} c_k.
 template <class CFG>
 MPC_DEV void riccati_factor(double *sm) {
     typedef SL<CFG> S;
-    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NT = MPC_NT;
-    double *W = sm + (N + 1) * S::STRIDE;
-    for (int k = N - 1; k >= 0; k--) {
-        double *st = sm + k * S::STRIDE;
-        double *stn = sm + (k + 1) * S::STRIDE;
-        // R1: split-K partial products  part[e][l] = BA[l][i] * (P+ BA)[l][j];  extra items: PC(k+1) = P_{k+1} c_k
-        MPC_PHASE
-        for (int it = tid; it < S::NPART + NX; it += NT) {
-            if (it < S::NPART) {
-                const int e = it / NX, l = it - e * NX;
-                int i = 0;
-                while ((i + 1) * (i + 2) / 2 <= e) i++;
-                const int j = e - i * (i + 1) / 2;  // i >= j
-                double wl = 0.0;
+    typedef RicIdx<CFG> R;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
+    static_assert(NU == 2, "input block is factorised in closed form for nu = 2");
+    MPC_PHASE
+    if (tid == 0) {
+        double Pn[S::NPP];
 #pragma unroll
-                for (int m = 0; m < NX; m++) wl += stn[S::P + trisym(l, m)] * st[S::BA + m * NZ + j];
-                W[S::W_PART + it] = st[S::BA + l * NZ + i] * wl;
-            } else {
-                const int r = it - S::NPART;
-                double acc = 0.0;
+        for (int e = 0; e < S::NPP; e++) Pn[e] = sm[N * S::STRIDE + S::P + e];
+        for (int k = N - 1; k >= 0; k--) {
+            double *st = sm + k * S::STRIDE;
+            double *stn = st + S::STRIDE;
+            double B[NX][NU], E[NX][NE], PB[NX][NU], PE[NX][NE];
 #pragma unroll
-                for (int m = 0; m < NX; m++) acc += stn[S::P + trisym(r, m)] * st[S::C + m];
-                stn[S::PC + r] = acc;
+            for (int l = 0; l < NX; l++) {
+#pragma unroll
+                for (int u = 0; u < NU; u++) B[l][u] = st[S::BA + l * NZ + u];
+#pragma unroll
+                for (int c = 0; c < NE; c++) E[l][c] = st[S::BA + l * NZ + NU + R::ecol(c)] - ((l == R::ecol(c)) ? 1.0 : 0.0);
             }
-        }
-        MPC_PHASE_END
-        // R1b: M = H + barrier terms + sum of partials
-        MPC_PHASE
-        for (int e = tid; e < S::NHP; e += NT) {
-            int i = 0;
-            while ((i + 1) * (i + 2) / 2 <= e) i++;
-            const int j = e - i * (i + 1) / 2;
-            double acc = st[S::H + e];
-            if (i == j) acc += st[S::GD + i];
-            {
-                const int ai = (i == CFG::IX) ? 0 : (i == CFG::IY) ? 1 : (i == CFG::IPSI) ? 2 : -1;
-                const int aj = (j == CFG::IX) ? 0 : (j == CFG::IY) ? 1 : (j == CFG::IPSI) ? 2 : -1;
-                if (ai >= 0 && aj >= 0) acc += st[S::GB + trisym(ai, aj)];
-                if (CFG::ANY_SLACK_ROWS) {
-                    if (i == CFG::ISLACK && aj >= 0) acc += st[S::GS + aj];
-                    if (i == CFG::ISLACK && j == CFG::ISLACK) acc += st[S::GS + 3];
+#pragma unroll
+            for (int l = 0; l < NX; l++) {
+                double pc = 0.0;
+#pragma unroll
+                for (int u = 0; u < NU; u++) PB[l][u] = 0.0;
+#pragma unroll
+                for (int c = 0; c < NE; c++) PE[l][c] = 0.0;
+#pragma unroll
+                for (int m = 0; m < NX; m++) {
+                    const double plm = Pn[trisym(l, m)];
+#pragma unroll
+                    for (int u = 0; u < NU; u++) PB[l][u] += plm * B[m][u];
+#pragma unroll
+                    for (int c = 0; c < NE; c++) PE[l][c] += plm * E[m][c];
+                    pc += plm * st[S::C + m];
                 }
+                stn[S::PC + l] = pc;
             }
+            // M_uu
+            double m00 = st[S::H + tri(0, 0)] + st[S::GD + 0], m10 = st[S::H + tri(1, 0)], m11 = st[S::H + tri(1, 1)] + st[S::GD + 1];
 #pragma unroll
-            for (int l = 0; l < NX; l++) acc += W[S::W_PART + e * NX + l];
-            W[S::W_M + e] = acc;
-        }
-        MPC_PHASE_END
-        // R2: Cholesky of M_uu (redundantly per thread), L_xu = M_xu L_uu^-T, P = M_xx - L_xu L_xu'
-        MPC_PHASE
-        if (tid < S::NPP + NX + 1) {
-            static_assert(NU == 2, "input block is factorised in closed form for nu = 2");
-            const double m00 = W[S::W_M + tri(0, 0)], m10 = W[S::W_M + tri(1, 0)], m11 = W[S::W_M + tri(1, 1)];
+            for (int l = 0; l < NX; l++) {
+                m00 += B[l][0] * PB[l][0];
+                m10 += B[l][1] * PB[l][0];
+                m11 += B[l][1] * PB[l][1];
+            }
             const double il00 = mpc_rsqrt(m00);
             const double l10 = m10 * il00;
             const double il11 = mpc_rsqrt(m11 - l10 * l10);
-            const int e = tid;
-            if (e < S::NPP) {
-                int i = 0;
-                while ((i + 1) * (i + 2) / 2 <= e) i++;
-                const int j = e - i * (i + 1) / 2;
-                const double li0 = W[S::W_M + tri(NU + i, 0)] * il00, li1 = (W[S::W_M + tri(NU + i, 1)] - li0 * l10) * il11;
-                const double lj0 = W[S::W_M + tri(NU + j, 0)] * il00, lj1 = (W[S::W_M + tri(NU + j, 1)] - lj0 * l10) * il11;
-                st[S::P + e] = W[S::W_M + tri(NU + i, NU + j)] - li0 * lj0 - li1 * lj1;
-            } else if (e < S::NPP + NX) {
-                const int i = e - S::NPP;
-                const double li0 = W[S::W_M + tri(NU + i, 0)] * il00, li1 = (W[S::W_M + tri(NU + i, 1)] - li0 * l10) * il11;
-                st[S::LXU + i * NU] = li0;
-                st[S::LXU + i * NU + 1] = li1;
-            } else {
-                st[S::LUU] = il00;
-                st[S::LUU + 1] = l10;
-                st[S::LUU + 2] = il11;
+            st[S::LUU] = il00;
+            st[S::LUU + 1] = l10;
+            st[S::LUU + 2] = il11;
+            // M_xu = H_xu + A' P B = H_xu + PB + E' PB (rows psi, v only);  L_xu = M_xu L_uu^-T
+            double Lx[NX][NU];
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+                double mx0 = st[S::H + tri(NU + i, 0)] + PB[i][0], mx1 = st[S::H + tri(NU + i, 1)] + PB[i][1];
+                if (R::eidx(i) >= 0) {
+#pragma unroll
+                    for (int l = 0; l < NX; l++) {
+                        mx0 += E[l][R::eidx(i) >= 0 ? R::eidx(i) : 0] * PB[l][0];
+                        mx1 += E[l][R::eidx(i) >= 0 ? R::eidx(i) : 0] * PB[l][1];
+                    }
+                }
+                Lx[i][0] = mx0 * il00;
+                Lx[i][1] = (mx1 - Lx[i][0] * l10) * il11;
+                st[S::LXU + i * NU] = Lx[i][0];
+                st[S::LXU + i * NU + 1] = Lx[i][1];
             }
+            // M_xx = H_xx + barrier + A' P A,  A' P A = P + PE Sel + Sel' PE' + Sel' (E' PE) Sel;  P = M_xx - L_xu L_xu'
+            double Pk[S::NPP];
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+#pragma unroll
+                for (int j = 0; j <= i; j++) {
+                    double acc = st[S::H + tri(NU + i, NU + j)] + Pn[tri(i, j)];
+                    if (i == j) acc += st[S::GD + NU + i];
+                    {
+                        const int ai = (NU + i == CFG::IX) ? 0 : (NU + i == CFG::IY) ? 1 : (NU + i == CFG::IPSI) ? 2 : -1;
+                        const int aj = (NU + j == CFG::IX) ? 0 : (NU + j == CFG::IY) ? 1 : (NU + j == CFG::IPSI) ? 2 : -1;
+                        if (ai >= 0 && aj >= 0) acc += st[S::GB + trisym(ai >= 0 ? ai : 0, aj >= 0 ? aj : 0)];
+                        if (CFG::ANY_SLACK_ROWS) {
+                            if (NU + i == CFG::ISLACK && aj >= 0) acc += st[S::GS + (aj >= 0 ? aj : 0)];
+                            if (NU + i == CFG::ISLACK && NU + j == CFG::ISLACK) acc += st[S::GS + 3];
+                        }
+                    }
+                    if (R::eidx(j) >= 0) acc += PE[i][R::eidx(j) >= 0 ? R::eidx(j) : 0];
+                    if (R::eidx(i) >= 0) acc += PE[j][R::eidx(i) >= 0 ? R::eidx(i) : 0];
+                    if (R::eidx(i) >= 0 && R::eidx(j) >= 0) {
+#pragma unroll
+                        for (int l = 0; l < NX; l++) acc += E[l][R::eidx(i) >= 0 ? R::eidx(i) : 0] * PE[l][R::eidx(j) >= 0 ? R::eidx(j) : 0];
+                    }
+                    acc -= Lx[i][0] * Lx[j][0] + Lx[i][1] * Lx[j][1];
+                    Pk[tri(i, j)] = acc;
+                    st[S::P + tri(i, j)] = acc;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < S::NPP; e++) Pn[e] = Pk[e];
         }
-        MPC_PHASE_END
     }
+    MPC_PHASE_END
 }
 
 // Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PIN.
 template <class CFG>
 MPC_DEV void riccati_solve(double *sm) {
     typedef SL<CFG> S;
-    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NT = MPC_NT;
+    typedef RicIdx<CFG> R;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
     double *W = sm + (N + 1) * S::STRIDE;
-    // terminal: pv_N = gt_N (x part lives at [NU, NZ) of the node layout); known dx_0
     MPC_PHASE
-    if (tid < NX) {
-        sm[N * S::STRIDE + S::PV + tid] = sm[N * S::STRIDE + S::GT + NU + tid];
-        sm[S::DZN + NU + tid] = W[S::W_DX0 + tid];
-    }
-    MPC_PHASE_END
-    for (int k = N - 1; k >= 0; k--) {
-        double *st = sm + k * S::STRIDE;
-        const double *stn = sm + (k + 1) * S::STRIDE;
-        MPC_PHASE
-        if (tid <= NX) {
-            // m = gt + BA'(pv+ + P+ c);  y = Luu^-1 m_u;  pv = m_x - Lxu y   (thread i < NX: row i; thread NX stores y)
+    if (tid == 0) {
+        // backward: m = gt + BA'(pv+ + P+ c);  y = Luu^-1 m_u;  pv = m_x - Lxu y
+        double pv[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+            pv[i] = sm[N * S::STRIDE + S::GT + NU + i];  // terminal: pv_N = gt_N
+            sm[N * S::STRIDE + S::PV + i] = pv[i];
+        }
+        for (int k = N - 1; k >= 0; k--) {
+            double *st = sm + k * S::STRIDE;
+            const double *stn = st + S::STRIDE;
             double q[NX];
 #pragma unroll
-            for (int l = 0; l < NX; l++) q[l] = stn[S::PV + l] + stn[S::PC + l];
+            for (int l = 0; l < NX; l++) q[l] = pv[l] + stn[S::PC + l];
             double m0 = st[S::GT + 0], m1 = st[S::GT + 1];
 #pragma unroll
             for (int l = 0; l < NX; l++) {
@@ -404,27 +440,29 @@ MPC_DEV void riccati_solve(double *sm) {
             }
             const double y0 = m0 * st[S::LUU];
             const double y1 = (m1 - st[S::LUU + 1] * y0) * st[S::LUU + 2];
-            if (tid < NX) {
-                double mx = st[S::GT + NU + tid];
+            st[S::YV] = y0;
+            st[S::YV + 1] = y1;
 #pragma unroll
-                for (int l = 0; l < NX; l++) mx += st[S::BA + l * NZ + NU + tid] * q[l];
-                st[S::PV + tid] = mx - st[S::LXU + tid * NU] * y0 - st[S::LXU + tid * NU + 1] * y1;
-            } else {
-                st[S::YV] = y0;
-                st[S::YV + 1] = y1;
+            for (int i = 0; i < NX; i++) {
+                double mx = st[S::GT + NU + i] + q[i];  // A = I + E
+                if (R::eidx(i) >= 0) {
+#pragma unroll
+                    for (int l = 0; l < NX; l++) mx += (st[S::BA + l * NZ + NU + i] - ((l == i) ? 1.0 : 0.0)) * q[l];
+                }
+                pv[i] = mx - st[S::LXU + i * NU] * y0 - st[S::LXU + i * NU + 1] * y1;
+                st[S::PV + i] = pv[i];
             }
         }
-        MPC_PHASE_END
-    }
-    for (int k = 0; k < N; k++) {
-        double *st = sm + k * S::STRIDE;
-        double *stn = sm + (k + 1) * S::STRIDE;
-        MPC_PHASE
-        if (tid <= NX) {
-            // du = -Luu^-T (y + Lxu' dx);  dx+ = c + B du + A dx   (thread i < NX: row i; thread NX stores du)
-            double dx[NX];
+        // forward: du = -Luu^-T (y + Lxu' dx);  dx+ = c + B du + A dx
+        double dx[NX];
 #pragma unroll
-            for (int l = 0; l < NX; l++) dx[l] = st[S::DZN + NU + l];
+        for (int i = 0; i < NX; i++) {
+            dx[i] = W[S::W_DX0 + i];
+            sm[S::DZN + NU + i] = dx[i];
+        }
+        for (int k = 0; k < N; k++) {
+            double *st = sm + k * S::STRIDE;
+            double *stn = st + S::STRIDE;
             double w0 = st[S::YV], w1 = st[S::YV + 1];
 #pragma unroll
             for (int l = 0; l < NX; l++) {
@@ -434,18 +472,22 @@ MPC_DEV void riccati_solve(double *sm) {
             const double il00 = st[S::LUU], l10 = st[S::LUU + 1], il11 = st[S::LUU + 2];
             const double k1 = w1 * il11;
             const double k0 = (w0 - l10 * k1) * il00;
-            if (tid < NX) {
-                double acc = st[S::C + tid] - st[S::BA + tid * NZ] * k0 - st[S::BA + tid * NZ + 1] * k1;
+            st[S::DZN] = -k0;
+            st[S::DZN + 1] = -k1;
+            double dxn[NX];
 #pragma unroll
-                for (int l = 0; l < NX; l++) acc += st[S::BA + tid * NZ + NU + l] * dx[l];
-                stn[S::DZN + NU + tid] = acc;
-            } else {
-                st[S::DZN] = -k0;
-                st[S::DZN + 1] = -k1;
+            for (int i = 0; i < NX; i++) {
+                double acc = st[S::C + i] + dx[i] - st[S::BA + i * NZ] * k0 - st[S::BA + i * NZ + 1] * k1;
+#pragma unroll
+                for (int c = 0; c < NE; c++) acc += (st[S::BA + i * NZ + NU + R::ecol(c)] - ((i == R::ecol(c)) ? 1.0 : 0.0)) * dx[R::ecol(c)];
+                dxn[i] = acc;
+                stn[S::DZN + NU + i] = acc;
             }
+#pragma unroll
+            for (int i = 0; i < NX; i++) dx[i] = dxn[i];
         }
-        MPC_PHASE_END
     }
+    MPC_PHASE_END
     // pi_k = P_k dx_k + pv_k  for k = 1..N, all in parallel
     MPC_PHASE
     for (int it = tid; it < N * NX; it += NT) {
