@@ -92,6 +92,10 @@ typedef struct mpcgpu_problem_desc {
     double reg_epsilon; /* MIRROR threshold (acados default 1e-4) */
     double qp_mu0;      /* IPM initial barrier (HPIPM BALANCE: 1e1) */
     double qp_thr0;     /* IPM initial slack floor (HPIPM: 1e-1) */
+    int qp_warm_start;  /* qp_solver_warm_start (generate_acados_solver.py:173: 2 = primal and dual): RTI iterations > 0
+                           start the IPM from the previous QP's multipliers */
+    double qp_ws_thr;   /* warm start: slack floor t = max(row value, qp_ws_thr) */
+    double qp_ws_mu;    /* warm start: multiplier floor lam = max(lam_prev, qp_ws_mu / t) */
     double res_eq_fail; /* res_eq above this demotes success (acados_solver_interface.cpp:176-181) */
 } mpcgpu_problem_desc;
 

@@ -66,6 +66,9 @@ inline Layout make_layout(const mpcgpu_problem_desc &d) {
     L.qp_mu0 = d.qp_mu0;
     L.qp_thr0 = d.qp_thr0;
     L.res_eq_fail = d.res_eq_fail;
+    L.qp_warm_start = d.qp_warm_start;
+    L.qp_ws_thr = d.qp_ws_thr;
+    L.qp_ws_mu = d.qp_ws_mu;
     return L;
 }
 

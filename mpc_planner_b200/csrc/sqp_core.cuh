@@ -29,9 +29,23 @@
 #define MPC_PHASE_END }
 #endif
 
+// Development aid (-DMPC_PROFILE, scripts/profile_phases.py): thread 0 accumulates clock64() per phase
+// category in shared memory and the kernel writes the totals over the first doubles of utraj.
+#if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
+#define MPC_TICK(cat)                                                  \
+    if (threadIdx.x == 0) {                                            \
+        const long long now__ = clock64();                             \
+        mpc_prof[cat] += (double)(now__ - (long long)mpc_prof[31]);    \
+        mpc_prof[31] = (double)now__;                                  \
+    }
+#else
+#define MPC_TICK(cat)
+#endif
+
 namespace mpcgpu {
 
 constexpr int MPC_NT = 128;  // threads per solve
+enum { TK_LIN = 0, TK_ASM, TK_INIT, TK_PA, TK_PB, TK_ACC0, TK_RED, TK_FACTOR, TK_SOLVE, TK_PD, TK_ACC1, TK_PF, TK_STEP, TK_FINAL };
 
 // parameter accessor over the per-solve transposed parameter block pt[npar][32] (column = stage)
 struct ParamT {
@@ -126,7 +140,8 @@ struct SL {
     static constexpr int W_RED2 = W_RED + 6 * MPC_NT;  // 6 x 32
     static constexpr int W_SC = W_RED2 + 6 * 32;       // scalars
     static constexpr int W_DX0 = W_SC + 16;     // NX
-    static constexpr int W_SIZE = W_DX0 + NX;
+    static constexpr int W_PROF = W_DX0 + NX;   // 32 doubles (profiling builds)
+    static constexpr int W_SIZE = W_PROF + 32;
     static constexpr int TOTAL = (CFG::N + 1) * STRIDE + W_SIZE;  // doubles per CTA
 };
 // scalar slots in W_SC
@@ -649,10 +664,12 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
 // 3 min step, 4 NaN) -- uniform across the CTA.
 // ---------------------------------------------------------------------------------------------
 template <class CFG>
-MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
+MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm) {
     typedef SL<CFG> S;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NROW = CFG::NROW, NT = MPC_NT;
     double *W = sm + (N + 1) * S::STRIDE;
+    double *mpc_prof = W + S::W_PROF;
+    (void)mpc_prof;
     const double T_MIN = 1e-10, LAM_MIN = 1e-16, ALPHA_MIN = 1e-12;
     // number of inequality rows in the QP (uniform)
     int nc = 0;
@@ -663,7 +680,8 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
     nc += NH * (N - 1);
     const double inv_nc = (nc > 0) ? 1.0 / nc : 0.0;
 
-    // cold start (HPIPM-style): dz = 0, pi = 0; t = max(r, thr0), lam = mu0 / t in the first row phase
+    // start: dz = 0, pi = 0; slacks / multipliers are initialised in the first row phase (cold: HPIPM-style
+    // t = max(r, thr0), lam = mu0 / t; warm: see there)
     MPC_PHASE
     for (int it = tid; it < (N + 1) * NZ; it += NT) {
         const int k = it / NZ, i = it - k * NZ;
@@ -677,6 +695,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
     }
     MPC_PHASE_END
 
+    MPC_TICK(TK_INIT)
     int status = 0, iter = 0;
     double alpha = 0.0, sigma_mu = 0.0;
     for (;; iter++) {
@@ -690,6 +709,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
                 if (k >= 1 && i < NX) st[S::DPI + i] += alpha * (st[S::PIN + i] - st[S::DPI + i]);
             }
             MPC_PHASE_END
+            MPC_TICK(TK_PA)
         }
         // ---- PB: rows: (init | step) of t, lam; 1/t; residual pieces ----
         MPC_PHASE
@@ -702,8 +722,13 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
                 const double cv = row_value<CFG>(L, st, r, st + S::DZ);
                 double tt, l;
                 if (iter == 0) {
-                    tt = fmax(cv, L.qp_thr0);
-                    l = L.qp_mu0 * mpc_rcp(tt);
+                    if (warm) {  // qp_solver_warm_start = 2: keep the previous QP's multipliers, re-centre the slacks
+                        tt = fmax(cv, L.qp_ws_thr);
+                        l = fmax(st[S::LAM + r], L.qp_ws_mu * mpc_rcp(tt));
+                    } else {
+                        tt = fmax(cv, L.qp_thr0);
+                        l = L.qp_mu0 * mpc_rcp(tt);
+                    }
                 } else {
                     const double cvn = row_value<CFG>(L, st, r, st + S::DZN);
                     const double t0 = st[S::T + r], l0 = st[S::LAM + r], ti = st[S::TINV + r];
@@ -725,12 +750,15 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
             W[S::W_RED + 4 * NT + tid] = musum;
         }
         MPC_PHASE_END
+        MPC_TICK(TK_PB)
         // ---- PC: stationarity / equality residuals, barrier Hessian terms, affine gradient ----
         stage_accumulate<CFG, 0>(L, sm, 0.0);
+        MPC_TICK(TK_ACC0)
         {
             const int kinds[5] = {0, 0, 0, 0, 1}, dst[5] = {SC_RS, SC_RE, SC_RI, SC_RC, SC_MU};
             block_reduce<CFG, 5>(W, kinds, dst);
         }
+        MPC_TICK(TK_RED)
         const double rs = W[S::W_SC + SC_RS], re = W[S::W_SC + SC_RE], ri = W[S::W_SC + SC_RI], rc = W[S::W_SC + SC_RC];
         const double mu = W[S::W_SC + SC_MU] * inv_nc;
 #if !defined(__CUDACC__) && defined(MPC_EMU_TRACE)
@@ -741,7 +769,9 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
         if (iter >= L.qp_iter_max) { status = 2; break; }
 
         riccati_factor<CFG>(sm);
+        MPC_TICK(TK_FACTOR)
         riccati_solve<CFG>(sm);
+        MPC_TICK(TK_SOLVE)
         sigma_mu = 0.0;
         if (nc > 0) {
             // ---- PD: affine step: ratio test, centering sums, second-order term ----
@@ -766,10 +796,12 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
                 W[S::W_RED + 2 * NT + tid] = s2;
             }
             MPC_PHASE_END
+            MPC_TICK(TK_PD)
             {
                 const int kinds[3] = {0, 1, 1}, dst[3] = {SC_RMAX, SC_S1, SC_S2};
                 block_reduce<CFG, 3>(W, kinds, dst);
             }
+            MPC_TICK(TK_RED)
             {
                 const double a_aff = 1.0 / fmax(1.0, W[S::W_SC + SC_RMAX]);
                 // mu_aff = sum (lam + a dl)(t + a dt) / nc = mu + a S1/nc + a^2 S2/nc
@@ -781,7 +813,9 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
             }
             // ---- PE: corrector gradient and solve ----
             stage_accumulate<CFG, 1>(L, sm, sigma_mu);
+            MPC_TICK(TK_ACC1)
             riccati_solve<CFG>(sm);
+            MPC_TICK(TK_SOLVE)
         }
         // ---- PF: step length to the boundary ----
         MPC_PHASE
@@ -800,10 +834,12 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out) {
             W[S::W_RED + tid] = rmax;
         }
         MPC_PHASE_END
+        MPC_TICK(TK_PF)
         {
             const int kinds[1] = {0}, dst[1] = {SC_RMAX};
             block_reduce<CFG, 1>(W, kinds, dst);
         }
+        MPC_TICK(TK_RED)
         alpha = 0.995 / fmax(1.0, W[S::W_SC + SC_RMAX]);  // fraction to the boundary; never a full step
         if (!(sigma_mu == sigma_mu) || !(alpha == alpha)) { status = 4; break; }
         if (alpha < ALPHA_MIN) { status = 3; break; }
@@ -824,6 +860,15 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NT = MPC_NT;
     static_assert(N + 1 <= 32, "parameters are staged in 32 columns");
     double *W = sm + (N + 1) * S::STRIDE;
+    double *mpc_prof = W + S::W_PROF;
+    (void)mpc_prof;
+#if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 32; i++) mpc_prof[i] = 0.0;
+        mpc_prof[31] = (double)clock64();
+    }
+    __syncthreads();
+#endif
     // loadWarmstart (acados_solver_interface.cpp:274-284): x (k = 0..N) and u (k < N) from x0;
     // fresh solver: zero multipliers
     MPC_PHASE
@@ -854,12 +899,14 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
             W[S::W_DX0 + i] = xinit[i] - sm[S::Z + NU + i];
         }
         MPC_PHASE_END
+        MPC_TICK(TK_LIN)
         MPC_PHASE
         if (tid < N) assemble_stage<CFG>(L, sm + tid * S::STRIDE);
         MPC_PHASE_END
+        MPC_TICK(TK_ASM)
         // feedback: QP
         int iters = 0;
-        qp_status = ipm_solve<CFG>(L, sm, &iters);
+        qp_status = ipm_solve<CFG>(L, sm, &iters, sq > 0 && L.qp_warm_start != 0);
         qp_iter_total += iters;
         sqp_iter = sq + 1;
         if (qp_status == 3 || qp_status == 4) break;  // QP failure: no step (acados sqp_rti)
@@ -877,6 +924,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
             }
         }
         MPC_PHASE_END
+        MPC_TICK(TK_STEP)
         if (qp_status != 0) break;  // Q4: the reference loop stops on any non-zero qp_status
     }
 
@@ -925,6 +973,11 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         info->qp_iter = qp_iter_total;
     }
     MPC_PHASE_END
+#if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
+    MPC_TICK(TK_FINAL)
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 16; i++) utraj[i] = mpc_prof[i];
+#endif
 }
 
 }  // namespace mpcgpu

@@ -64,6 +64,9 @@ class ProblemDesc(ctypes.Structure):
         ("reg_epsilon", ctypes.c_double),
         ("qp_mu0", ctypes.c_double),
         ("qp_thr0", ctypes.c_double),
+        ("qp_warm_start", ctypes.c_int),
+        ("qp_ws_thr", ctypes.c_double),
+        ("qp_ws_mu", ctypes.c_double),
         ("res_eq_fail", ctypes.c_double),
     ]
 
@@ -126,6 +129,9 @@ class ProblemSpec:
     reg_epsilon: float = 1e-4  # acados default reg_epsilon for MIRROR (:157)
     qp_mu0: float = 1e1
     qp_thr0: float = 1e-1
+    qp_warm_start: int = 2  # generate_acados_solver.py:173
+    qp_ws_thr: float = 1e-2
+    qp_ws_mu: float = 1e-3
     res_eq_fail: float = 1e-2  # acados_solver_interface.cpp:176
 
     # ---- model_map ----
@@ -280,6 +286,7 @@ class ProblemSpec:
         d.n_sqp, d.qp_iter_max, d.qp_tol = self.n_sqp, self.qp_iter_max, self.qp_tol
         d.reg_epsilon, d.qp_mu0, d.qp_thr0 = self.reg_epsilon, self.qp_mu0, self.qp_thr0
         d.res_eq_fail = self.res_eq_fail
+        d.qp_warm_start, d.qp_ws_thr, d.qp_ws_mu = self.qp_warm_start, self.qp_ws_thr, self.qp_ws_mu
         return d
 
     # sizes of the reference's flat arrays (AcadosParameters, acados_solver_interface.h:51-56)

@@ -7,9 +7,12 @@
 #include <cstring>
 #include <vector>
 
+namespace mpcgpu { extern long g_mirror_slow, g_mirror_calls; }
 #include "../../mpc_planner_b200/csrc/registry.cuh"
 
+namespace mpcgpu { long g_mirror_slow = 0, g_mirror_calls = 0; }
 using namespace mpcgpu;
+extern "C" void emu_mirror_stats(long *calls, long *slow) { *calls = g_mirror_calls; *slow = g_mirror_slow; }
 
 template <class CFG>
 static int solve_cfg(const mpcgpu_problem_desc &d, int P, const double *xinit, const double *x0, const double *params,
