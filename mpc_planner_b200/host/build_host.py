@@ -1,0 +1,22 @@
+"""Build the C++ host layer (MPCPlanner::Solver over the C ABI) and its test for one problem."""
+import os
+import subprocess
+
+from .. import build as libbuild
+from .. import problem as pb
+from ..generate import generate_solver
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build_test(name="cfg2", out_dir=None):
+    spec = pb.CONFIGS[name]()
+    out_dir = out_dir or os.path.join(HERE, "generated", name)
+    generate_solver(spec, out_dir)
+    exe = os.path.join(out_dir, "test_solver")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I" + out_dir, "-I" + os.path.join(HERE, "include"), "-I" + os.path.join(libbuild.ROOT, "include"),
+           os.path.join(HERE, "src", "cuda_solver_interface.cpp"), os.path.join(HERE, "test", "test_solver.cpp"),
+           "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-o", exe]
+    subprocess.check_call(cmd)
+    return exe

@@ -233,6 +233,32 @@ class ProblemSpec:
     def npar(self) -> int:
         return len(self.parameter_map())
 
+    def parameter_bundles(self) -> Dict[str, List[int]]:
+        """bundle name -> parameter indices, as `Parameters.parameter_bundles` of the reference
+        (util/parameters.py:46-53): the generated C++ `setSolverParameter<Bundle>(k, params, value, index)`
+        setters are keyed by these (generate_cpp_files.py:235-254)."""
+        import re
+
+        rules = [
+            (r"^spline_([xy])\d+_([abcd])$", lambda m: f"spline_{m.group(1)}_{m.group(2)}"),
+            (r"^spline\d+_start$", lambda m: "spline_start"),
+            (r"^lin_constraint_\d+_(a1|a2|b)$", lambda m: f"lin_constraint_{m.group(1)}"),
+            (r"^ego_disc_\d+_offset$", lambda m: "ego_disc_offset"),
+            (r"^ellipsoid_obst_\d+_(\w+)$", lambda m: f"ellipsoid_obst_{m.group(1)}"),
+            (r"^gaussian_obst_\d+_(\w+)$", lambda m: f"gaussian_obst_{m.group(1)}"),
+            (r"^disc_\d+_decomp_\d+_(a1|a2|b)$", lambda m: f"decomp_{m.group(1)}"),
+        ]
+        bundles: Dict[str, List[int]] = {}
+        for name, idx in self.parameter_map().items():
+            bundle = name  # scenario constraints and scalar weights are their own bundle
+            for pat, fn in rules:
+                m = re.match(pat, name)
+                if m:
+                    bundle = fn(m)
+                    break
+            bundles.setdefault(bundle, []).append(idx)
+        return bundles
+
     def constraint_first_param(self) -> List[int]:
         pm = self.parameter_map()
         first = {

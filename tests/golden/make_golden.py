@@ -194,7 +194,7 @@ def main(M=24):
             f = [float(v) for v in model.continuous_model(z[model.nu:], z[: model.nu])]
             samples.append(dict(z=z.tolist(), p=p.tolist(), cost=l1, h=h, f=f))
         out[name] = dict(
-            parameter_map=pmap, npar=params.length(), nh=nh, lh=lh, uh=uh, nx=model.nx, nu=model.nu,
+            parameter_map=pmap, parameter_bundles={k: [int(i) for i in v] for k, v in params.parameter_bundles.items()}, npar=params.length(), nh=nh, lh=lh, uh=uh, nx=model.nx, nu=model.nu,
             states=model.states, inputs=model.inputs, lower_bound=list(map(float, model.lower_bound)),
             upper_bound=list(map(float, model.upper_bound)), samples=samples,
         )

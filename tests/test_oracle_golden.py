@@ -19,6 +19,7 @@ SPECS = {
 def test_parameter_map_matches_reference(golden, name):
     spec, g = SPECS[name], golden[name]
     assert spec.parameter_map() == g["parameter_map"]
+    assert spec.parameter_bundles() == g["parameter_bundles"]
     assert spec.npar == g["npar"] and spec.nh == g["nh"]
     assert spec.nx == g["nx"] and spec.nu == g["nu"]
     assert spec.states == g["states"] and spec.inputs == g["inputs"]
