@@ -146,10 +146,10 @@ def calibrate_threads(spec, batch):
     """Pick the OpenMP thread count that solves a small sample fastest (hyper-threads / cgroup quotas
     make 'all logical CPUs' a bad default on some boxes)."""
     cores = usable_cores()
-    cands = sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True)
+    cands = sorted({cores, max(1, cores // 2)}, reverse=True)
     best_t, best_rate = cands[0], 0.0
     for t in cands:
-        n = min(len(batch["xinit"]), max(4 * t, 32))
+        n = len(batch["xinit"])  # the whole pool: small samples are dominated by the slowest solve
         cpu_solve_pass(spec, batch, min(n, t), t)  # spin the team up
         dt, _ = cpu_solve_pass(spec, batch, n, t)
         if n / dt > best_rate:
