@@ -140,7 +140,9 @@ struct SL {
     static constexpr int W_RED2 = W_RED + 6 * MPC_NT;  // 6 x 32
     static constexpr int W_SC = W_RED2 + 6 * 32;       // scalars
     static constexpr int W_DX0 = W_SC + 16;     // NX
-    static constexpr int W_PROF = W_DX0 + NX;   // 32 doubles (profiling builds)
+    static constexpr int W_LB = W_DX0 + NX;     // NZ lower bounds (copy of Layout, for dynamic indexing)
+    static constexpr int W_UB = W_LB + NZ;      // NZ upper bounds
+    static constexpr int W_PROF = W_UB + NZ;    // 32 doubles (profiling builds)
     static constexpr int W_SIZE = W_PROF + 32;
     static constexpr int TOTAL = (CFG::N + 1) * STRIDE + W_SIZE;  // doubles per CTA
 };
@@ -315,6 +317,12 @@ struct RicIdx {
     static constexpr int NE = 2;  // columns of A that differ from the identity: psi, v
     MPC_HD static constexpr int ecol(int c) { return c == 0 ? 2 : 3; }  // x-index of psi, v
     MPC_HD static constexpr int eidx(int xi) { return xi == 2 ? 0 : (xi == 3 ? 1 : -1); }
+    // structural non-zeros of the discrete dynamics of the unicycle family (stage_functions.cuh,
+    // unicycle_step): rows x=0, y=1, psi=2, v=3, spline=4 (, slack=5: identity row)
+    //   E = A - I :  column psi: rows x, y ;  column v: rows x, y, spline
+    //   B         :  column a: rows x, y, v, spline ;  column w: rows x, y, psi
+    MPC_HD static constexpr bool enz(int l, int c) { return c == 0 ? (l == 0 || l == 1) : (l == 0 || l == 1 || l == 4); }
+    MPC_HD static constexpr bool bnz(int l, int u) { return u == 0 ? (l == 0 || l == 1 || l == 3 || l == 4) : (l == 0 || l == 1 || l == 2); }
 };
 
 // Backward factorisation: for k = N-1..0   M = H + barrier terms + [B A]' P+ [B A];
@@ -352,9 +360,11 @@ MPC_DEV void riccati_factor(double *sm) {
                 for (int m = 0; m < NX; m++) {
                     const double plm = Pn[trisym(l, m)];
 #pragma unroll
-                    for (int u = 0; u < NU; u++) PB[l][u] += plm * B[m][u];
+                    for (int u = 0; u < NU; u++)
+                        if (R::bnz(m, u)) PB[l][u] += plm * B[m][u];
 #pragma unroll
-                    for (int c = 0; c < NE; c++) PE[l][c] += plm * E[m][c];
+                    for (int c = 0; c < NE; c++)
+                        if (R::enz(m, c)) PE[l][c] += plm * E[m][c];
                     pc += plm * st[S::C + m];
                 }
                 stn[S::PC + l] = pc;
@@ -363,9 +373,9 @@ MPC_DEV void riccati_factor(double *sm) {
             double m00 = st[S::H + tri(0, 0)] + st[S::GD + 0], m10 = st[S::H + tri(1, 0)], m11 = st[S::H + tri(1, 1)] + st[S::GD + 1];
 #pragma unroll
             for (int l = 0; l < NX; l++) {
-                m00 += B[l][0] * PB[l][0];
-                m10 += B[l][1] * PB[l][0];
-                m11 += B[l][1] * PB[l][1];
+                if (R::bnz(l, 0)) m00 += B[l][0] * PB[l][0];
+                if (R::bnz(l, 1)) m10 += B[l][1] * PB[l][0];
+                if (R::bnz(l, 1)) m11 += B[l][1] * PB[l][1];
             }
             const double il00 = mpc_rsqrt(m00);
             const double l10 = m10 * il00;
@@ -381,6 +391,7 @@ MPC_DEV void riccati_factor(double *sm) {
                 if (R::eidx(i) >= 0) {
 #pragma unroll
                     for (int l = 0; l < NX; l++) {
+                        if (!R::enz(l, R::eidx(i) >= 0 ? R::eidx(i) : 0)) continue;
                         mx0 += E[l][R::eidx(i) >= 0 ? R::eidx(i) : 0] * PB[l][0];
                         mx1 += E[l][R::eidx(i) >= 0 ? R::eidx(i) : 0] * PB[l][1];
                     }
@@ -411,7 +422,8 @@ MPC_DEV void riccati_factor(double *sm) {
                     if (R::eidx(i) >= 0) acc += PE[j][R::eidx(i) >= 0 ? R::eidx(i) : 0];
                     if (R::eidx(i) >= 0 && R::eidx(j) >= 0) {
 #pragma unroll
-                        for (int l = 0; l < NX; l++) acc += E[l][R::eidx(i) >= 0 ? R::eidx(i) : 0] * PE[l][R::eidx(j) >= 0 ? R::eidx(j) : 0];
+                        for (int l = 0; l < NX; l++)
+                            if (R::enz(l, R::eidx(i) >= 0 ? R::eidx(i) : 0)) acc += E[l][R::eidx(i) >= 0 ? R::eidx(i) : 0] * PE[l][R::eidx(j) >= 0 ? R::eidx(j) : 0];
                     }
                     acc -= Lx[i][0] * Lx[j][0] + Lx[i][1] * Lx[j][1];
                     Pk[tri(i, j)] = acc;
@@ -450,8 +462,8 @@ MPC_DEV void riccati_solve(double *sm) {
             double m0 = st[S::GT + 0], m1 = st[S::GT + 1];
 #pragma unroll
             for (int l = 0; l < NX; l++) {
-                m0 += st[S::BA + l * NZ + 0] * q[l];
-                m1 += st[S::BA + l * NZ + 1] * q[l];
+                if (R::bnz(l, 0)) m0 += st[S::BA + l * NZ + 0] * q[l];
+                if (R::bnz(l, 1)) m1 += st[S::BA + l * NZ + 1] * q[l];
             }
             const double y0 = m0 * st[S::LUU];
             const double y1 = (m1 - st[S::LUU + 1] * y0) * st[S::LUU + 2];
@@ -462,7 +474,8 @@ MPC_DEV void riccati_solve(double *sm) {
                 double mx = st[S::GT + NU + i] + q[i];  // A = I + E
                 if (R::eidx(i) >= 0) {
 #pragma unroll
-                    for (int l = 0; l < NX; l++) mx += (st[S::BA + l * NZ + NU + i] - ((l == i) ? 1.0 : 0.0)) * q[l];
+                    for (int l = 0; l < NX; l++)
+                        if (R::enz(l, R::eidx(i) >= 0 ? R::eidx(i) : 0)) mx += st[S::BA + l * NZ + NU + i] * q[l];  // l != i on the pattern
                 }
                 pv[i] = mx - st[S::LXU + i * NU] * y0 - st[S::LXU + i * NU + 1] * y1;
                 st[S::PV + i] = pv[i];
@@ -492,9 +505,12 @@ MPC_DEV void riccati_solve(double *sm) {
             double dxn[NX];
 #pragma unroll
             for (int i = 0; i < NX; i++) {
-                double acc = st[S::C + i] + dx[i] - st[S::BA + i * NZ] * k0 - st[S::BA + i * NZ + 1] * k1;
+                double acc = st[S::C + i] + dx[i];
+                if (R::bnz(i, 0)) acc -= st[S::BA + i * NZ] * k0;
+                if (R::bnz(i, 1)) acc -= st[S::BA + i * NZ + 1] * k1;
 #pragma unroll
-                for (int c = 0; c < NE; c++) acc += (st[S::BA + i * NZ + NU + R::ecol(c)] - ((i == R::ecol(c)) ? 1.0 : 0.0)) * dx[R::ecol(c)];
+                for (int c = 0; c < NE; c++)
+                    if (R::enz(i, c)) acc += st[S::BA + i * NZ + NU + R::ecol(c)] * dx[R::ecol(c)];  // i != ecol(c) on the pattern
                 dxn[i] = acc;
                 stn[S::DZN + NU + i] = acc;
             }
@@ -660,6 +676,115 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row phases of the IPM: thread = (stage, variable) for the two box rows of a variable and
+// thread = (stage, h row) for the general rows -- class-specific straight-line code, no divergence
+// between row kinds inside a warp.
+//   RP_UPDATE : (init | step) of t, lam; 1/t; inequality / complementarity residuals, sum lam t
+//   RP_AFFINE : ratio test of the affine step, centering sums S1, S2, second-order term
+//   RP_STEP   : ratio test of the combined step
+// ---------------------------------------------------------------------------------------------
+enum { RP_UPDATE = 0, RP_AFFINE = 1, RP_STEP = 2 };
+
+struct RowCtx {
+    // inputs
+    bool first, warm;
+    double alpha, sigma_mu, thr0, mu0, ws_thr, ws_mu;
+    // accumulators
+    double a0, a1, a2;
+};
+
+template <class CFG, int MODE>
+MPC_HD void row_body(double *st, int r, double cv, double cvn, RowCtx &c) {
+    typedef SL<CFG> S;
+    const double T_MIN = 1e-10, LAM_MIN = 1e-16;
+    if (MODE == RP_UPDATE) {
+        double tt, l;
+        if (c.first) {
+            if (c.warm) {  // qp_solver_warm_start = 2: keep the previous QP's multipliers, re-centre the slacks
+                tt = fmax(cv, c.ws_thr);
+                l = fmax(st[S::LAM + r], c.ws_mu * mpc_rcp(tt));
+            } else {
+                tt = fmax(cv, c.thr0);
+                l = c.mu0 * mpc_rcp(tt);
+            }
+        } else {
+            const double t0 = st[S::T + r], l0 = st[S::LAM + r], ti = st[S::TINV + r];
+            const double dt = cvn - t0;
+            const double dl = (c.sigma_mu - st[S::CORR + r]) * ti - l0 * ti * cvn;
+            tt = fmax(t0 + c.alpha * dt, T_MIN);
+            l = fmax(l0 + c.alpha * dl, LAM_MIN);
+        }
+        st[S::T + r] = tt;
+        st[S::LAM + r] = l;
+        st[S::TINV + r] = mpc_rcp(tt);
+        st[S::CORR + r] = 0.0;
+        upd_max(c.a0, fabs(cv - tt));  // inequality residual
+        upd_max(c.a1, fabs(l * tt));   // complementarity residual
+        c.a2 += l * tt;
+    } else if (MODE == RP_AFFINE) {
+        const double tt = st[S::T + r], l = st[S::LAM + r], ti = st[S::TINV + r];
+        const double dt = cvn - tt;
+        const double dl = -l * ti * cvn;                 // sigma mu = corr = 0
+        c.a0 = fmax(c.a0, fmax(-dt * ti, ti * cvn));     // -dl/lam = cvn/t
+        c.a1 += l * dt + tt * dl;
+        c.a2 += dt * dl;
+        st[S::CORR + r] = dt * dl;
+    } else {
+        const double tt = st[S::T + r], l = st[S::LAM + r], ti = st[S::TINV + r];
+        const double dt = cvn - tt;
+        const double dl = (c.sigma_mu - st[S::CORR + r]) * ti - l * ti * cvn;
+        c.a0 = fmax(c.a0, fmax(-dt * ti, -dl * mpc_rcp(l)));
+    }
+}
+
+template <class CFG, int MODE>
+MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
+    typedef SL<CFG> S;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NU = CFG::NU, NH = CFG::NH, NT = MPC_NT;
+    double *W = sm + (N + 1) * S::STRIDE;
+    MPC_PHASE
+    {
+        RowCtx c = ctx;
+        c.a0 = c.a1 = c.a2 = 0.0;
+        // boxes: both rows of variable i of stage k (x0 is fixed: no state box at node 0)
+        for (int it = tid; it < N * NZ; it += NT) {
+            const int k = it / NZ, i = it - k * NZ;
+            if (k == 0 && i >= NU) continue;
+            double *st = sm + k * S::STRIDE;
+            const double lb = W[S::W_LB + i], ub = W[S::W_UB + i];
+            const double z = st[S::Z + i], v = st[S::DZ + i], vn = st[S::DZN + i];
+            if (lb > -1e10) row_body<CFG, MODE>(st, i, z - lb + v, z - lb + vn, c);
+            if (ub < 1e10) row_body<CFG, MODE>(st, NZ + i, ub - z - v, ub - z - vn, c);
+        }
+        // general rows of stages 1..N-1
+        for (int it = tid; it < (N - 1) * NH; it += NT) {
+            const int k = 1 + it / (NH > 0 ? NH : 1), j = it - (k - 1) * NH;
+            double *st = sm + k * S::STRIDE;
+            const double j0 = st[S::JR + 3 * j], j1 = st[S::JR + 3 * j + 1], j2 = st[S::JR + 3 * j + 2], rh = st[S::RH + j];
+            double cv = rh + j0 * st[S::DZ + CFG::IX] + j1 * st[S::DZ + CFG::IY] + j2 * st[S::DZ + CFG::IPSI];
+            double cvn = rh + j0 * st[S::DZN + CFG::IX] + j1 * st[S::DZN + CFG::IY] + j2 * st[S::DZN + CFG::IPSI];
+            if (CFG::ANY_SLACK_ROWS && row_has_slack<CFG>(j)) {
+                cv += st[S::DZ + (CFG::HAS_SLACK ? CFG::ISLACK : 0)];
+                cvn += st[S::DZN + (CFG::HAS_SLACK ? CFG::ISLACK : 0)];
+            }
+            row_body<CFG, MODE>(st, 2 * NZ + j, cv, cvn, c);
+        }
+        if (MODE == RP_UPDATE) {
+            W[S::W_RED + 2 * NT + tid] = c.a0;
+            W[S::W_RED + 3 * NT + tid] = c.a1;
+            W[S::W_RED + 4 * NT + tid] = c.a2;
+        } else {
+            W[S::W_RED + 0 * NT + tid] = c.a0;
+            if (MODE == RP_AFFINE) {
+                W[S::W_RED + 1 * NT + tid] = c.a1;
+                W[S::W_RED + 2 * NT + tid] = c.a2;
+            }
+        }
+    }
+    MPC_PHASE_END
+}
+
+// ---------------------------------------------------------------------------------------------
 // Interior-point QP solve.  Returns the QP status (acados numbering: 0 ok, 2 max iter,
 // 3 min step, 4 NaN) -- uniform across the CTA.
 // ---------------------------------------------------------------------------------------------
@@ -712,44 +837,18 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm) {
             MPC_TICK(TK_PA)
         }
         // ---- PB: rows: (init | step) of t, lam; 1/t; residual pieces ----
-        MPC_PHASE
         {
-            double ri = 0.0, rc = 0.0, musum = 0.0;
-            for (int it = tid; it < N * NROW; it += NT) {
-                const int k = it / NROW, r = it - k * NROW;
-                double *st = sm + k * S::STRIDE;
-                if (!row_active<CFG>(L, k, r)) continue;
-                const double cv = row_value<CFG>(L, st, r, st + S::DZ);
-                double tt, l;
-                if (iter == 0) {
-                    if (warm) {  // qp_solver_warm_start = 2: keep the previous QP's multipliers, re-centre the slacks
-                        tt = fmax(cv, L.qp_ws_thr);
-                        l = fmax(st[S::LAM + r], L.qp_ws_mu * mpc_rcp(tt));
-                    } else {
-                        tt = fmax(cv, L.qp_thr0);
-                        l = L.qp_mu0 * mpc_rcp(tt);
-                    }
-                } else {
-                    const double cvn = row_value<CFG>(L, st, r, st + S::DZN);
-                    const double t0 = st[S::T + r], l0 = st[S::LAM + r], ti = st[S::TINV + r];
-                    const double dt = cvn - t0;
-                    const double dl = (sigma_mu - st[S::CORR + r]) * ti - l0 * ti * cvn;
-                    tt = fmax(t0 + alpha * dt, T_MIN);
-                    l = fmax(l0 + alpha * dl, LAM_MIN);
-                }
-                st[S::T + r] = tt;
-                st[S::LAM + r] = l;
-                st[S::TINV + r] = mpc_rcp(tt);
-                st[S::CORR + r] = 0.0;
-                upd_max(ri, fabs(cv - tt));
-                upd_max(rc, fabs(l * tt));
-                musum += l * tt;
-            }
-            W[S::W_RED + 2 * NT + tid] = ri;
-            W[S::W_RED + 3 * NT + tid] = rc;
-            W[S::W_RED + 4 * NT + tid] = musum;
+            RowCtx c;
+            c.first = (iter == 0);
+            c.warm = warm;
+            c.alpha = alpha;
+            c.sigma_mu = sigma_mu;
+            c.thr0 = L.qp_thr0;
+            c.mu0 = L.qp_mu0;
+            c.ws_thr = L.qp_ws_thr;
+            c.ws_mu = L.qp_ws_mu;
+            rows_phase<CFG, RP_UPDATE>(L, sm, c);
         }
-        MPC_PHASE_END
         MPC_TICK(TK_PB)
         // ---- PC: stationarity / equality residuals, barrier Hessian terms, affine gradient ----
         stage_accumulate<CFG, 0>(L, sm, 0.0);
@@ -775,27 +874,14 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm) {
         sigma_mu = 0.0;
         if (nc > 0) {
             // ---- PD: affine step: ratio test, centering sums, second-order term ----
-            MPC_PHASE
             {
-                double rmax = 0.0, s1 = 0.0, s2 = 0.0;
-                for (int it = tid; it < N * NROW; it += NT) {
-                    const int k = it / NROW, r = it - k * NROW;
-                    double *st = sm + k * S::STRIDE;
-                    if (!row_active<CFG>(L, k, r)) continue;
-                    const double cvn = row_value<CFG>(L, st, r, st + S::DZN);
-                    const double tt = st[S::T + r], l = st[S::LAM + r], ti = st[S::TINV + r];
-                    const double dt = cvn - tt;
-                    const double dl = -l * ti * cvn;  // sigma mu = corr = 0
-                    rmax = fmax(rmax, fmax(-dt * ti, ti * cvn));  // -dl/lam = cvn/t
-                    s1 += l * dt + tt * dl;
-                    s2 += dt * dl;
-                    st[S::CORR + r] = dt * dl;
-                }
-                W[S::W_RED + 0 * NT + tid] = rmax;
-                W[S::W_RED + 1 * NT + tid] = s1;
-                W[S::W_RED + 2 * NT + tid] = s2;
+                RowCtx c;
+                c.first = false;
+                c.warm = false;
+                c.alpha = 0.0;
+                c.sigma_mu = 0.0;
+                rows_phase<CFG, RP_AFFINE>(L, sm, c);
             }
-            MPC_PHASE_END
             MPC_TICK(TK_PD)
             {
                 const int kinds[3] = {0, 1, 1}, dst[3] = {SC_RMAX, SC_S1, SC_S2};
@@ -818,22 +904,14 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm) {
             MPC_TICK(TK_SOLVE)
         }
         // ---- PF: step length to the boundary ----
-        MPC_PHASE
         {
-            double rmax = 0.0;
-            for (int it = tid; it < N * NROW; it += NT) {
-                const int k = it / NROW, r = it - k * NROW;
-                double *st = sm + k * S::STRIDE;
-                if (!row_active<CFG>(L, k, r)) continue;
-                const double cvn = row_value<CFG>(L, st, r, st + S::DZN);
-                const double tt = st[S::T + r], l = st[S::LAM + r], ti = st[S::TINV + r];
-                const double dt = cvn - tt;
-                const double dl = (sigma_mu - st[S::CORR + r]) * ti - l * ti * cvn;
-                rmax = fmax(rmax, fmax(-dt * ti, -dl * mpc_rcp(l)));
-            }
-            W[S::W_RED + tid] = rmax;
+            RowCtx c;
+            c.first = false;
+            c.warm = false;
+            c.alpha = 0.0;
+            c.sigma_mu = sigma_mu;
+            rows_phase<CFG, RP_STEP>(L, sm, c);
         }
-        MPC_PHASE_END
         MPC_TICK(TK_PF)
         {
             const int kinds[1] = {0}, dst[1] = {SC_RMAX};
@@ -882,6 +960,10 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
             if (o - S::P == tri(i, i)) v = L.reg_epsilon;
         }
         sm[it] = v;
+    }
+    if (tid < NZ) {
+        W[S::W_LB + tid] = L.lower_bound[tid];
+        W[S::W_UB + tid] = L.upper_bound[tid];
     }
     MPC_PHASE_END
 

@@ -79,3 +79,26 @@ def test_scene_generator_invariants():
                 assert bb == pytest.approx(a1 * ox + a2 * oy - (1e-3 + scenes.ROBOT_RADIUS))
                 dist = np.hypot(ox - x0[i, k, nu], oy - x0[i, k, nu + 1])
                 assert a1 * x0[i, k, nu] + a2 * x0[i, k, nu + 1] - bb == pytest.approx(-dist + 1e-3 + scenes.ROBOT_RADIUS)
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_structural_sparsity_assumed_by_the_riccati_sweeps(golden, name):
+    """csrc/sqp_core.cuh (RicIdx) hard-codes the non-zero pattern of [B A] of the unicycle family;
+    check it against the actual Jacobians."""
+    spec, g = SPECS[name], golden[name]
+    d = spec.desc()
+    nx, nu = spec.nx, spec.nu
+    enz = lambda l, c: (l in (0, 1)) if c == 0 else (l in (0, 1, 4))  # noqa: E731
+    bnz = lambda l, u: (l in (0, 1, 3, 4)) if u == 0 else (l in (0, 1, 2))  # noqa: E731
+    for s in g["samples"][:8]:
+        AB = emu.eval_stage(d, np.array(s["z"]), np.array(s["p"]))["AB"][0]
+        B, A = AB[:, :nu], AB[:, nu:]
+        E = A - np.eye(nx)
+        for l in range(nx):
+            for u in range(nu):
+                if not bnz(l, u):
+                    assert B[l, u] == 0.0
+            for j in range(nx):
+                c = {2: 0, 3: 1}.get(j, -1)
+                if c < 0 or not enz(l, c):
+                    assert E[l, j] == 0.0
