@@ -45,6 +45,13 @@
 namespace mpcgpu {
 
 constexpr int MPC_NT = 128;  // threads per solve
+// partials per reduced quantity: one per warp on the device (threads pre-reduce with shuffles),
+// one per thread in the host emulation
+#if defined(__CUDACC__)
+constexpr int MPC_RED_SLOTS = MPC_NT / 32;
+#else
+constexpr int MPC_RED_SLOTS = MPC_NT;
+#endif
 enum { TK_LIN = 0, TK_ASM, TK_INIT, TK_PA, TK_PB, TK_ACC0, TK_RED, TK_FACTOR, TK_SOLVE, TK_PD, TK_ACC1, TK_PF, TK_STEP, TK_FINAL };
 
 // parameter accessor over the per-solve transposed parameter block pt[npar][32] (column = stage)
@@ -136,9 +143,8 @@ struct SL {
     static constexpr int NPART = NHP * NX;      // split-K partial products of the Riccati M matrix
     static constexpr int W_PART = 0;
     static constexpr int W_M = W_PART + NPART;  // NHP: M matrix of the stage being factorised
-    static constexpr int W_RED = W_M + NHP;     // 6 x NT reduction staging
-    static constexpr int W_RED2 = W_RED + 6 * MPC_NT;  // 6 x 32
-    static constexpr int W_SC = W_RED2 + 6 * 32;       // scalars
+    static constexpr int W_RED = W_M + NHP;     // reduction staging: 6 quantities x RED_SLOTS partials
+    static constexpr int W_SC = W_RED + 6 * MPC_RED_SLOTS;  // scalars
     static constexpr int W_DX0 = W_SC + 16;     // NX
     static constexpr int W_LB = W_DX0 + NX;     // NZ lower bounds (copy of Layout, for dynamic indexing)
     static constexpr int W_UB = W_LB + NZ;      // NZ upper bounds
@@ -179,8 +185,10 @@ MPC_HD double row_value(const Layout &L, const double *st, int r, const double *
 }
 
 // ---------------------------------------------------------------------------------------------
-// CTA reductions over per-thread partials staged in W_RED[q][tid], q < NQ.  kinds: 0 max (NaN
-// propagating), 1 sum.  Result of quantity q is written to W_SC[dst[q]].
+// CTA reductions.  kinds: 0 max (NaN propagating), 1 sum.  `red_put` is called by EVERY thread
+// inside the producing phase (device: warp-shuffle pre-reduction, lane 0 stores one partial per
+// warp; emulation: one partial per thread); after the phase barrier `red_get` combines the
+// partials (redundantly in every thread: no second barrier).
 // ---------------------------------------------------------------------------------------------
 MPC_HD double red_combine(int kind, double a, double b) {
     if (kind == 1) return a + b;
@@ -188,34 +196,25 @@ MPC_HD double red_combine(int kind, double a, double b) {
     return (b != b || b > a) ? b : a;
 }
 
-template <class CFG, int NQ>
-MPC_DEV void block_reduce(double *W, const int *kinds, const int *dst) {
+template <class CFG>
+MPC_DEV void red_put(double *W, int tid, int q, int kind, double v) {
     typedef SL<CFG> S;
-    constexpr int NT = MPC_NT;
-    MPC_PHASE
-    if (tid < 32) {
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            double v = W[S::W_RED + q * NT + tid];
-#pragma unroll
-            for (int w = 1; w < NT / 32; w++) v = red_combine(kinds[q], v, W[S::W_RED + q * NT + tid + 32 * w]);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v = red_combine(kinds[q], v, __shfl_xor_sync(0xffffffffu, v, off));
-            if (tid == 0) W[S::W_SC + dst[q]] = v;
+    for (int off = 16; off > 0; off >>= 1) v = red_combine(kind, v, __shfl_xor_sync(0xffffffffu, v, off));
+    if ((tid & 31) == 0) W[S::W_RED + q * MPC_RED_SLOTS + (tid >> 5)] = v;
 #else
-            W[S::W_RED2 + q * 32 + tid] = v;
+    W[S::W_RED + q * MPC_RED_SLOTS + tid] = v;
 #endif
-        }
-    }
-    MPC_PHASE_END
-#if !defined(__CUDA_ARCH__)
-    for (int q = 0; q < NQ; q++) {
-        double v = W[S::W_RED2 + q * 32];
-        for (int i = 1; i < 32; i++) v = red_combine(kinds[q], v, W[S::W_RED2 + q * 32 + i]);
-        W[S::W_SC + dst[q]] = v;
-    }
-#endif
+}
+
+template <class CFG>
+MPC_DEV double red_get(const double *W, int q, int kind) {
+    typedef SL<CFG> S;
+    double v = W[S::W_RED + q * MPC_RED_SLOTS];
+#pragma unroll
+    for (int i = 1; i < MPC_RED_SLOTS; i++) v = red_combine(kind, v, W[S::W_RED + q * MPC_RED_SLOTS + i]);
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -668,8 +667,8 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
             }
         }
         if (MODE == 0) {
-            W[S::W_RED + 0 * NT + tid] = rs;
-            W[S::W_RED + 1 * NT + tid] = re;
+            red_put<CFG>(W, tid, 0, 0, rs);
+            red_put<CFG>(W, tid, 1, 0, re);
         }
     }
     MPC_PHASE_END
@@ -770,14 +769,14 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
             row_body<CFG, MODE>(st, 2 * NZ + j, cv, cvn, c);
         }
         if (MODE == RP_UPDATE) {
-            W[S::W_RED + 2 * NT + tid] = c.a0;
-            W[S::W_RED + 3 * NT + tid] = c.a1;
-            W[S::W_RED + 4 * NT + tid] = c.a2;
+            red_put<CFG>(W, tid, 2, 0, c.a0);
+            red_put<CFG>(W, tid, 3, 0, c.a1);
+            red_put<CFG>(W, tid, 4, 1, c.a2);
         } else {
-            W[S::W_RED + 0 * NT + tid] = c.a0;
+            red_put<CFG>(W, tid, 0, 0, c.a0);
             if (MODE == RP_AFFINE) {
-                W[S::W_RED + 1 * NT + tid] = c.a1;
-                W[S::W_RED + 2 * NT + tid] = c.a2;
+                red_put<CFG>(W, tid, 1, 1, c.a1);
+                red_put<CFG>(W, tid, 2, 1, c.a2);
             }
         }
     }
@@ -789,7 +788,7 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
 // 3 min step, 4 NaN) -- uniform across the CTA.
 // ---------------------------------------------------------------------------------------------
 template <class CFG>
-MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm) {
+MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, double *res_out) {
     typedef SL<CFG> S;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NROW = CFG::NROW, NT = MPC_NT;
     double *W = sm + (N + 1) * S::STRIDE;
@@ -853,13 +852,11 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm) {
         // ---- PC: stationarity / equality residuals, barrier Hessian terms, affine gradient ----
         stage_accumulate<CFG, 0>(L, sm, 0.0);
         MPC_TICK(TK_ACC0)
-        {
-            const int kinds[5] = {0, 0, 0, 0, 1}, dst[5] = {SC_RS, SC_RE, SC_RI, SC_RC, SC_MU};
-            block_reduce<CFG, 5>(W, kinds, dst);
-        }
+        const double rs = red_get<CFG>(W, 0, 0), re = red_get<CFG>(W, 1, 0), ri = red_get<CFG>(W, 2, 0), rc = red_get<CFG>(W, 3, 0);
+        const double mu = red_get<CFG>(W, 4, 1) * inv_nc;
+        res_out[0] = rs;
+        res_out[1] = rc;
         MPC_TICK(TK_RED)
-        const double rs = W[S::W_SC + SC_RS], re = W[S::W_SC + SC_RE], ri = W[S::W_SC + SC_RI], rc = W[S::W_SC + SC_RC];
-        const double mu = W[S::W_SC + SC_MU] * inv_nc;
 #if !defined(__CUDACC__) && defined(MPC_EMU_TRACE)
         if (getenv("EMU_DEBUG")) fprintf(stderr, "  ipm %2d: stat %.3e eq %.3e ineq %.3e comp %.3e mu %.3e\n", iter, rs, re, ri, rc, mu);
 #endif
@@ -884,14 +881,9 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm) {
             }
             MPC_TICK(TK_PD)
             {
-                const int kinds[3] = {0, 1, 1}, dst[3] = {SC_RMAX, SC_S1, SC_S2};
-                block_reduce<CFG, 3>(W, kinds, dst);
-            }
-            MPC_TICK(TK_RED)
-            {
-                const double a_aff = 1.0 / fmax(1.0, W[S::W_SC + SC_RMAX]);
+                const double a_aff = 1.0 / fmax(1.0, red_get<CFG>(W, 0, 0));
                 // mu_aff = sum (lam + a dl)(t + a dt) / nc = mu + a S1/nc + a^2 S2/nc
-                const double mu_aff = mu + a_aff * (W[S::W_SC + SC_S1] + a_aff * W[S::W_SC + SC_S2]) * inv_nc;
+                const double mu_aff = mu + a_aff * (red_get<CFG>(W, 1, 1) + a_aff * red_get<CFG>(W, 2, 1)) * inv_nc;
                 const double ratio = (mu > 0.0) ? mu_aff / mu : 0.0;
                 // Mehrotra centering, floored at a fraction of the complementarity tolerance: driving mu far
                 // below qp_tol only makes lam/t huge and buries the stationarity residual in round-off
@@ -913,12 +905,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm) {
             rows_phase<CFG, RP_STEP>(L, sm, c);
         }
         MPC_TICK(TK_PF)
-        {
-            const int kinds[1] = {0}, dst[1] = {SC_RMAX};
-            block_reduce<CFG, 1>(W, kinds, dst);
-        }
-        MPC_TICK(TK_RED)
-        alpha = 0.995 / fmax(1.0, W[S::W_SC + SC_RMAX]);  // fraction to the boundary; never a full step
+        alpha = 0.995 / fmax(1.0, red_get<CFG>(W, 0, 0));  // fraction to the boundary; never a full step
         if (!(sigma_mu == sigma_mu) || !(alpha == alpha)) { status = 4; break; }
         if (alpha < ALPHA_MIN) { status = 3; break; }
     }
@@ -968,6 +955,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     MPC_PHASE_END
 
     int qp_status = 0, sqp_iter = 0, qp_iter_total = 0;
+    double qp_res[2] = {0.0, 0.0};  // last QP: stationarity / complementarity residuals
     for (int sq = 0; sq < L.n_sqp; sq++) {
         // preparation: linearise every stage at the current iterate
         MPC_PHASE
@@ -983,12 +971,15 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         MPC_PHASE_END
         MPC_TICK(TK_LIN)
         MPC_PHASE
-        if (tid < N) assemble_stage<CFG>(L, sm + tid * S::STRIDE);
+        {   // stages spread over the warps (lanes 0..ceil(N/4)-1 of each): MIRROR's Jacobi sweeps diverge per stage
+            const int k = (tid & 31) * (NT / 32) + (tid >> 5);
+            if ((tid & 31) < (N + NT / 32 - 1) / (NT / 32) && k < N) assemble_stage<CFG>(L, sm + k * S::STRIDE);
+        }
         MPC_PHASE_END
         MPC_TICK(TK_ASM)
         // feedback: QP
         int iters = 0;
-        qp_status = ipm_solve<CFG>(L, sm, &iters, sq > 0 && L.qp_warm_start != 0);
+        qp_status = ipm_solve<CFG>(L, sm, &iters, sq > 0 && L.qp_warm_start != 0, qp_res);
         qp_iter_total += iters;
         sqp_iter = sq + 1;
         if (qp_status == 3 || qp_status == 4) break;  // QP failure: no step (acados sqp_rti)
@@ -1031,24 +1022,20 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         }
         for (int it = tid; it < (N + 1) * NX; it += NT) xtraj[it] = sm[(it / NX) * S::STRIDE + S::Z + NU + it % NX];
         for (int it = tid; it < N * NU; it += NT) utraj[it] = sm[(it / NU) * S::STRIDE + S::Z + it % NU];
-        W[S::W_RED + tid] = c;
-        W[S::W_RED + NT + tid] = defect;
+        red_put<CFG>(W, tid, 0, 1, c);
+        red_put<CFG>(W, tid, 1, 0, defect);
     }
     MPC_PHASE_END
-    {
-        const int kinds[2] = {1, 0}, dst[2] = {SC_S1, SC_S2};
-        block_reduce<CFG, 2>(W, kinds, dst);
-    }
     MPC_PHASE
     if (tid == 0) {
-        const double pobj = W[S::W_SC + SC_S1], res_eq = W[S::W_SC + SC_S2];
+        const double pobj = red_get<CFG>(W, 0, 1), res_eq = red_get<CFG>(W, 1, 0);
         int exit_code = 1;
         if (qp_status == 3 || qp_status == 4) exit_code = 4;  // ACADOS_QP_FAILURE
         if (!(res_eq <= L.res_eq_fail) && exit_code == 1) exit_code = 4;  // acados_solver_interface.cpp:176-181
         info->pobj = pobj;
         info->res_eq = res_eq;
-        info->res_stat_qp = W[S::W_SC + SC_RS];
-        info->res_comp_qp = W[S::W_SC + SC_RC];
+        info->res_stat_qp = qp_res[0];
+        info->res_comp_qp = qp_res[1];
         info->exit_code = exit_code;
         info->qp_status = qp_status;
         info->sqp_iter = sqp_iter;
