@@ -96,6 +96,9 @@ typedef struct mpcgpu_problem_desc {
                            start the IPM from the previous QP's multipliers */
     double qp_ws_thr;   /* warm start: slack floor t = max(row value, qp_ws_thr) */
     double qp_ws_mu;    /* warm start: multiplier floor lam = max(lam_prev, qp_ws_mu / t) */
+    double qp_relax;    /* every inequality row is relaxed by this amount (1e-7) so that rows pinned exactly at their
+                           bound (the slack state of the slack models: zero dynamics, x0 = 0 = lower bound) keep an
+                           interior; same purpose as IPOPT's bound_relax_factor */
     double res_eq_fail; /* res_eq above this demotes success (acados_solver_interface.cpp:176-181) */
 } mpcgpu_problem_desc;
 

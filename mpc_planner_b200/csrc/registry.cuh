@@ -69,6 +69,7 @@ inline Layout make_layout(const mpcgpu_problem_desc &d) {
     L.qp_warm_start = d.qp_warm_start;
     L.qp_ws_thr = d.qp_ws_thr;
     L.qp_ws_mu = d.qp_ws_mu;
+    L.qp_relax = d.qp_relax;
     return L;
 }
 

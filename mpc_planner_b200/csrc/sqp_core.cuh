@@ -259,7 +259,7 @@ MPC_HD void linearize_part(const PA &pa, const Layout &L, double *st, const doub
             for (int j = lo; j < hi; j++) {  // fold the bound side: row value s (h - bound) >= 0, gradient s dh
                 const int kind = row_kind<CFG>(j);
                 const double sgn = row_sign<CFG>(kind);
-                st[S::RH + j] = sgn * (st[S::RH + j] - row_bound<CFG>(kind));
+                st[S::RH + j] = sgn * (st[S::RH + j] - row_bound<CFG>(kind)) + L.qp_relax;
                 st[S::JR + 3 * j] *= sgn;
                 st[S::JR + 3 * j + 1] *= sgn;
                 st[S::JR + 3 * j + 2] *= sgn;
@@ -585,7 +585,7 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
                     const double gam = l * ti;
                     rg -= l;
                     gd += gam;
-                    gt -= l - gam * (st[S::Z + i] - L.lower_bound[i]);
+                    gt -= l - gam * (st[S::Z + i] - L.lower_bound[i] + L.qp_relax);
                 } else {
                     gt -= (sigma_mu - st[S::CORR + i]) * ti;
                 }
@@ -596,7 +596,7 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
                     const double gam = l * ti;
                     rg += l;
                     gd += gam;
-                    gt += l - gam * (L.upper_bound[i] - st[S::Z + i]);
+                    gt += l - gam * (L.upper_bound[i] - st[S::Z + i] + L.qp_relax);
                 } else {
                     gt += (sigma_mu - st[S::CORR + NZ + i]) * ti;
                 }
@@ -752,8 +752,9 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
             double *st = sm + k * S::STRIDE;
             const double lb = W[S::W_LB + i], ub = W[S::W_UB + i];
             const double z = st[S::Z + i], v = st[S::DZ + i], vn = st[S::DZN + i];
-            if (lb > -1e10) row_body<CFG, MODE>(st, i, z - lb + v, z - lb + vn, c);
-            if (ub < 1e10) row_body<CFG, MODE>(st, NZ + i, ub - z - v, ub - z - vn, c);
+            // rows are relaxed by qp_relax (see mpcgpu.h): an interior exists even for rows pinned at their bound
+            if (lb > -1e10) row_body<CFG, MODE>(st, i, z - lb + v + L.qp_relax, z - lb + vn + L.qp_relax, c);
+            if (ub < 1e10) row_body<CFG, MODE>(st, NZ + i, ub - z - v + L.qp_relax, ub - z - vn + L.qp_relax, c);
         }
         // general rows of stages 1..N-1
         for (int it = tid; it < (N - 1) * NH; it += NT) {

@@ -67,6 +67,7 @@ class ProblemDesc(ctypes.Structure):
         ("qp_warm_start", ctypes.c_int),
         ("qp_ws_thr", ctypes.c_double),
         ("qp_ws_mu", ctypes.c_double),
+        ("qp_relax", ctypes.c_double),
         ("res_eq_fail", ctypes.c_double),
     ]
 
@@ -132,6 +133,7 @@ class ProblemSpec:
     qp_warm_start: int = 2  # generate_acados_solver.py:173
     qp_ws_thr: float = 1e-2
     qp_ws_mu: float = 1e-3
+    qp_relax: float = 1e-7
     res_eq_fail: float = 1e-2  # acados_solver_interface.cpp:176
 
     # ---- model_map ----
@@ -313,6 +315,7 @@ class ProblemSpec:
         d.reg_epsilon, d.qp_mu0, d.qp_thr0 = self.reg_epsilon, self.qp_mu0, self.qp_thr0
         d.res_eq_fail = self.res_eq_fail
         d.qp_warm_start, d.qp_ws_thr, d.qp_ws_mu = self.qp_warm_start, self.qp_ws_thr, self.qp_ws_mu
+        d.qp_relax = self.qp_relax
         return d
 
     # sizes of the reference's flat arrays (AcadosParameters, acados_solver_interface.h:51-56)

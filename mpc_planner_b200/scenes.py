@@ -223,7 +223,7 @@ def make_scene_batch(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int, seed: 
         if n_dec:
             n_sides = min(8, n_dec)
             rot = rng.uniform(0, 2 * np.pi)
-            widths = rng.uniform(1.5, 3.0, n_sides)
+            widths = rng.uniform(3.5, 5.0, n_sides)  # corridor wide enough to contain every guess (max lateral offset 3 m)
             for k in range(1, N):
                 for i in range(n_sides):
                     th = rot + 2 * np.pi * i / n_sides
@@ -302,7 +302,7 @@ def make_scene_batch(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int, seed: 
                     rows = []
                     for o in range(n_obs):
                         mode = srng.random(64) < 0.6
-                        spread = 0.15 + 0.1 * t[k]
+                        spread = 0.05 + 0.05 * t[k]
                         turn = np.where(mode, 0.0, np.deg2rad(30.0) * np.sign(srng.standard_normal(64)))
                         rel = obs_pos[o, k] - obs_pos[o, 0]
                         c, s_ = np.cos(turn), np.sin(turn)
@@ -312,8 +312,10 @@ def make_scene_batch(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int, seed: 
                         dist = np.linalg.norm(dv, axis=1)
                         a = dv / dist[:, None]
                         b = np.einsum("ij,ij->i", a, samp) - (OBSTACLE_RADIUS + ROBOT_RADIUS)
-                        rows.append(np.column_stack([a, b, b - a @ pk]))
-                    rows = np.concatenate(rows)
+                        margin = b - a @ pk  # > 0: the guess satisfies the halfspace
+                        keep_mask = margin > 0.05  # scenarios the guess already violates are discarded (removed as support)
+                        rows.append(np.column_stack([a, b, margin])[keep_mask])
+                    rows = np.concatenate(rows) if rows else np.zeros((0, 4))
                     keep = rows[np.argsort(rows[:, 3])[:n_sce]]
                     for i, r in enumerate(keep):
                         par[k, pm[f"disc_0_scenario_constraint_{i}_a1"]] = r[0]

@@ -36,7 +36,7 @@ def test_hand_derived_derivatives_match_oracle_ad(golden, name):
             np.testing.assert_allclose(e[key][0], ref, rtol=1e-10, atol=1e-11 * (1 + np.abs(ref).max()), err_msg=key)
 
 
-@pytest.mark.parametrize("name,S,P", [("cfg2", 3, 8), ("cfg1", 6, 1), ("cfg2_gaussian", 2, 4)])
+@pytest.mark.parametrize("name,S,P", [("cfg2", 3, 8), ("cfg1", 6, 1), ("cfg2_gaussian", 2, 4), ("cfg3", 2, 4), ("cfg4", 2, 4)])
 def test_emulated_kernel_solves_match_oracle(name, S, P):
     spec = SPECS[name]
     b = scenes.make_scene_batch(spec, S, P, seed=31)

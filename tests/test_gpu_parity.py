@@ -67,7 +67,7 @@ def _compare(spec, batch, xt, ut, info, best, rtol=1e-6):
     return n_ok
 
 
-@pytest.mark.parametrize("name,scenes_guesses", [("cfg2", (4, 8)), ("cfg1", (8, 1)), ("cfg2_gaussian", (2, 8))])
+@pytest.mark.parametrize("name,scenes_guesses", [("cfg2", (4, 8)), ("cfg1", (8, 1)), ("cfg2_gaussian", (2, 8)), ("cfg3", (2, 8)), ("cfg4", (4, 4))])
 def test_solve_matches_oracle(binding, name, scenes_guesses):
     spec = SPECS[name]
     S, P = scenes_guesses
