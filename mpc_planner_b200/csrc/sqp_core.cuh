@@ -102,24 +102,25 @@ template <class CFG>
 struct SL {
     static constexpr int NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NROW = CFG::NROW;
     static constexpr int NHP = NZ * (NZ + 1) / 2, NPP = NX * (NX + 1) / 2;
+    static constexpr int NE = 2;                // columns of A that differ from the identity (psi, v)
     static constexpr int Z = 0;                 // NLP iterate [u;x]
-    static constexpr int PI = Z + NZ;           // NLP multiplier of the equation defining x_k
-    static constexpr int LAM = PI + NX;         // inequality multipliers (IPM variable = NLP multiplier after the QP)
+    static constexpr int LAM = Z + NZ;          // inequality multipliers (IPM variable = NLP multiplier after the QP)
     static constexpr int T = LAM + NROW;        // IPM slacks
     static constexpr int TINV = T + NROW;       // 1/t
     static constexpr int CORR = TINV + NROW;    // Mehrotra second-order term dt_aff * dlam_aff
     static constexpr int H = CORR + NROW;       // regularised Hessian block, packed lower
     static constexpr int GR = H + NHP;          // QP gradient
-    static constexpr int BA = GR + NZ;          // [B A], row-major NX x NZ
-    static constexpr int C = BA + NX * NZ;      // Phi(x,u) - x_next
+    static constexpr int BB = GR + NZ;          // B, row-major NX x NU
+    static constexpr int BE = BB + NX * NU;     // E = A - I, its non-zero columns (psi, v), row-major NX x NE
+    static constexpr int C = BE + NX * NE;      // Phi(x,u) - x_next
     static constexpr int JR = C + NX;           // sign-folded rows of dh/d(x,y,psi), NH x 3
-    static constexpr int RH = JR + 3 * NH;      // sign-folded h residual s (h - bound)
+    static constexpr int RH = JR + 3 * NH;      // sign-folded h residual s (h - bound) + relaxation
     // ---- IPM / Riccati work area (also used as scratch by the linearisation) ----
     static constexpr int WK = RH + NH;
     static constexpr int GD = WK;               // barrier Hessian: diagonal part
     static constexpr int GB = GD + NZ;          //   (x,y,psi) block, packed lower 6
-    static constexpr int GS = GB + 6;           //   slack cross terms (x,y,psi,slack)
-    static constexpr int GT = GS + 4;           // barrier-modified gradient
+    static constexpr int GS = GB + 6;           //   slack cross terms (x,y,psi,slack); only for slack rows
+    static constexpr int GT = GS + (CFG::ANY_SLACK_ROWS ? 4 : 0);  // barrier-modified gradient
     static constexpr int P = GT + NZ;           // Riccati cost-to-go matrix, packed lower
     static constexpr int PC = P + NPP;          // P_k c_{k-1}
     static constexpr int PV = PC + NX;          // Riccati cost-to-go vector
@@ -127,33 +128,43 @@ struct SL {
     static constexpr int LXU = YV + NU;         // L_xu = M_xu L_uu^-T, NX x NU
     static constexpr int LUU = LXU + NU * NX;   // Cholesky factor of M_uu as {1/l00, l10, 1/l11}
     static constexpr int DZ = LUU + 3;          // QP primal iterate
-    static constexpr int DPI = DZ + NZ;         // QP equality multiplier iterate
+    static constexpr int DPI = DZ + NZ;         // equality multipliers: QP iterate during the IPM, NLP multiplier pi_k
+                                                // of the equation defining x_k between QPs (read by the linearisation)
+    static constexpr int PI = DPI;
     static constexpr int DZN = DPI + NX;        // Newton target (primal)
     static constexpr int PIN = DZN + NZ;        // Newton target (equality multiplier)
     static constexpr int RAW = PIN + NX;
     static constexpr int STRIDE = RAW | 1;      // odd
-    // linearisation scratch inside the work area (dead while linearising): partial Hessians
+    // linearisation scratch inside the work area (dead while linearising): partial Hessians.  It must not touch
+    // DPI (= pi, read by the dynamics part of the NEXT stage's... of this stage's predecessor)
     static constexpr int LS_HC = WK;            // cost Hessian (packed lower NZ)   -- written by the cost part
     static constexpr int LS_GC = LS_HC + NHP;   // cost gradient NZ
     static constexpr int LS_HD = LS_GC + NZ;    // dynamics Hessian entries (7)
     static constexpr int LS_HX = LS_HD + 7;     // constraint Hessian parts: 4 x 6
     static constexpr int LS_END = LS_HX + 24;
-    static_assert(LS_END <= RAW, "linearisation scratch must fit in the IPM work area (stages k < N only)");
-    // per-CTA scratch after the (N+1) stages
-    static constexpr int NPART = NHP * NX;      // split-K partial products of the Riccati M matrix
-    static constexpr int W_PART = 0;
-    static constexpr int W_M = W_PART + NPART;  // NHP: M matrix of the stage being factorised
-    static constexpr int W_RED = W_M + NHP;     // reduction staging: 6 quantities x RED_SLOTS partials
-    static constexpr int W_SC = W_RED + 6 * MPC_RED_SLOTS;  // scalars
-    static constexpr int W_DX0 = W_SC + 16;     // NX
+    static_assert(LS_END <= DPI, "linearisation scratch must stay below the multipliers pi (stages k < N only)");
+    // per-CTA scratch.  On the device it lives inside the terminal stage's unused rows area ([LAM, WK): the terminal
+    // node has no inequality rows, Hessian, dynamics or constraints); the host emulation needs one reduction slot per
+    // thread and keeps it after the stages.
+    static constexpr int W_RED = 0;             // reduction staging: 6 quantities x RED_SLOTS partials
+    static constexpr int W_DX0 = W_RED + 6 * MPC_RED_SLOTS;  // NX
     static constexpr int W_LB = W_DX0 + NX;     // NZ lower bounds (copy of Layout, for dynamic indexing)
     static constexpr int W_UB = W_LB + NZ;      // NZ upper bounds
     static constexpr int W_PROF = W_UB + NZ;    // 32 doubles (profiling builds)
+#if defined(MPC_PROFILE)
     static constexpr int W_SIZE = W_PROF + 32;
-    static constexpr int TOTAL = (CFG::N + 1) * STRIDE + W_SIZE;  // doubles per CTA
+#else
+    static constexpr int W_SIZE = W_PROF;
+#endif
+#if defined(__CUDACC__)
+    static constexpr int W_BASE = CFG::N * STRIDE + LAM;
+    static_assert(W_SIZE <= WK - LAM, "CTA scratch must fit in the terminal stage's unused area");
+    static constexpr int TOTAL = (CFG::N + 1) * STRIDE;  // doubles per CTA
+#else
+    static constexpr int W_BASE = (CFG::N + 1) * STRIDE;
+    static constexpr int TOTAL = (CFG::N + 1) * STRIDE + W_SIZE;
+#endif
 };
-// scalar slots in W_SC
-enum { SC_MU = 0, SC_SIGMU, SC_ALPHA, SC_RS, SC_RE, SC_RI, SC_RC, SC_S1, SC_S2, SC_RMAX };
 
 template <class CFG>
 MPC_HD bool box_active(const Layout &L, int k, int i, bool upper) {
@@ -244,7 +255,7 @@ MPC_HD void linearize_part(const PA &pa, const Layout &L, double *st, const doub
         double xn[NX], pin[NX], Hd[7];
 #pragma unroll
         for (int i = 0; i < NX; i++) pin[i] = st_next[S::PI + i];
-        unicycle_step<CFG>(L, z, xn, st + S::BA, pin, Hd);
+        unicycle_step<CFG>(L, z, xn, nullptr, pin, Hd, st + S::BB, st + S::BE);
 #pragma unroll
         for (int i = 0; i < 7; i++) st[S::LS_HD + i] = Hd[i];
 #pragma unroll
@@ -344,9 +355,9 @@ MPC_DEV void riccati_factor(double *sm) {
 #pragma unroll
             for (int l = 0; l < NX; l++) {
 #pragma unroll
-                for (int u = 0; u < NU; u++) B[l][u] = st[S::BA + l * NZ + u];
+                for (int u = 0; u < NU; u++) B[l][u] = st[S::BB + l * NU + u];
 #pragma unroll
-                for (int c = 0; c < NE; c++) E[l][c] = st[S::BA + l * NZ + NU + R::ecol(c)] - ((l == R::ecol(c)) ? 1.0 : 0.0);
+                for (int c = 0; c < NE; c++) E[l][c] = st[S::BE + l * NE + c];
             }
 #pragma unroll
             for (int l = 0; l < NX; l++) {
@@ -442,7 +453,7 @@ MPC_DEV void riccati_solve(double *sm) {
     typedef SL<CFG> S;
     typedef RicIdx<CFG> R;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
-    double *W = sm + (N + 1) * S::STRIDE;
+    double *W = sm + S::W_BASE;
     MPC_PHASE
     if (tid == 0) {
         // backward: m = gt + BA'(pv+ + P+ c);  y = Luu^-1 m_u;  pv = m_x - Lxu y
@@ -461,8 +472,8 @@ MPC_DEV void riccati_solve(double *sm) {
             double m0 = st[S::GT + 0], m1 = st[S::GT + 1];
 #pragma unroll
             for (int l = 0; l < NX; l++) {
-                if (R::bnz(l, 0)) m0 += st[S::BA + l * NZ + 0] * q[l];
-                if (R::bnz(l, 1)) m1 += st[S::BA + l * NZ + 1] * q[l];
+                if (R::bnz(l, 0)) m0 += st[S::BB + l * NU + 0] * q[l];
+                if (R::bnz(l, 1)) m1 += st[S::BB + l * NU + 1] * q[l];
             }
             const double y0 = m0 * st[S::LUU];
             const double y1 = (m1 - st[S::LUU + 1] * y0) * st[S::LUU + 2];
@@ -474,7 +485,7 @@ MPC_DEV void riccati_solve(double *sm) {
                 if (R::eidx(i) >= 0) {
 #pragma unroll
                     for (int l = 0; l < NX; l++)
-                        if (R::enz(l, R::eidx(i) >= 0 ? R::eidx(i) : 0)) mx += st[S::BA + l * NZ + NU + i] * q[l];  // l != i on the pattern
+                        if (R::enz(l, R::eidx(i) >= 0 ? R::eidx(i) : 0)) mx += st[S::BE + l * NE + (R::eidx(i) >= 0 ? R::eidx(i) : 0)] * q[l];
                 }
                 pv[i] = mx - st[S::LXU + i * NU] * y0 - st[S::LXU + i * NU + 1] * y1;
                 st[S::PV + i] = pv[i];
@@ -505,11 +516,11 @@ MPC_DEV void riccati_solve(double *sm) {
 #pragma unroll
             for (int i = 0; i < NX; i++) {
                 double acc = st[S::C + i] + dx[i];
-                if (R::bnz(i, 0)) acc -= st[S::BA + i * NZ] * k0;
-                if (R::bnz(i, 1)) acc -= st[S::BA + i * NZ + 1] * k1;
+                if (R::bnz(i, 0)) acc -= st[S::BB + i * NU] * k0;
+                if (R::bnz(i, 1)) acc -= st[S::BB + i * NU + 1] * k1;
 #pragma unroll
                 for (int c = 0; c < NE; c++)
-                    if (R::enz(i, c)) acc += st[S::BA + i * NZ + NU + R::ecol(c)] * dx[R::ecol(c)];  // i != ecol(c) on the pattern
+                    if (R::enz(i, c)) acc += st[S::BE + i * NE + c] * dx[R::ecol(c)];
                 dxn[i] = acc;
                 stn[S::DZN + NU + i] = acc;
             }
@@ -542,7 +553,7 @@ template <class CFG, int MODE>
 MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
     typedef SL<CFG> S;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NT = MPC_NT;
-    double *W = sm + (N + 1) * S::STRIDE;
+    double *W = sm + S::W_BASE;
     MPC_PHASE
     {
         double rs = 0.0, re = 0.0;
@@ -571,8 +582,18 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
 #pragma unroll
                     for (int j = 0; j < NZ; j++) rg += st[S::H + trisym(i, j)] * st[S::DZ + j];
                     const double *stn = sm + (k + 1) * S::STRIDE;
+                    // (BA' dpi+)_i with A = I + E
+                    if (i < NU) {
 #pragma unroll
-                    for (int l = 0; l < NX; l++) rg += st[S::BA + l * NZ + i] * stn[S::DPI + l];
+                        for (int l = 0; l < NX; l++) rg += st[S::BB + l * NU + i] * stn[S::DPI + l];
+                    } else {
+                        rg += stn[S::DPI + i - NU];
+                        const int ce = (i - NU == 2) ? 0 : ((i - NU == 3) ? 1 : -1);
+                        if (ce >= 0) {
+#pragma unroll
+                            for (int l = 0; l < NX; l++) rg += st[S::BE + l * S::NE + ce] * stn[S::DPI + l];
+                        }
+                    }
                 } else {
                     rg = L.reg_epsilon * st[S::DZ + i];  // H_N = eps I, g_N = 0
                 }
@@ -661,7 +682,8 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
                     const double *stn = sm + (k + 1) * S::STRIDE;
                     double acc = st[S::C + r] - stn[S::DZ + NU + r];
 #pragma unroll
-                    for (int j = 0; j < NZ; j++) acc += st[S::BA + r * NZ + j] * st[S::DZ + j];
+                    for (int u = 0; u < NU; u++) acc += st[S::BB + r * NU + u] * st[S::DZ + u];
+                    acc += st[S::DZ + NU + r] + st[S::BE + r * S::NE] * st[S::DZ + NU + 2] + st[S::BE + r * S::NE + 1] * st[S::DZ + NU + 3];
                     upd_max(re, fabs(acc));
                 }
             }
@@ -740,7 +762,7 @@ template <class CFG, int MODE>
 MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
     typedef SL<CFG> S;
     constexpr int N = CFG::N, NZ = CFG::NZ, NU = CFG::NU, NH = CFG::NH, NT = MPC_NT;
-    double *W = sm + (N + 1) * S::STRIDE;
+    double *W = sm + S::W_BASE;
     MPC_PHASE
     {
         RowCtx c = ctx;
@@ -792,7 +814,7 @@ template <class CFG>
 MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, double *res_out) {
     typedef SL<CFG> S;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NROW = CFG::NROW, NT = MPC_NT;
-    double *W = sm + (N + 1) * S::STRIDE;
+    double *W = sm + S::W_BASE;
     double *mpc_prof = W + S::W_PROF;
     (void)mpc_prof;
     const double T_MIN = 1e-10, LAM_MIN = 1e-16, ALPHA_MIN = 1e-12;
@@ -925,7 +947,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     typedef SL<CFG> S;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NT = MPC_NT;
     static_assert(N + 1 <= 32, "parameters are staged in 32 columns");
-    double *W = sm + (N + 1) * S::STRIDE;
+    double *W = sm + S::W_BASE;
     double *mpc_prof = W + S::W_PROF;
     (void)mpc_prof;
 #if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
@@ -949,6 +971,8 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         }
         sm[it] = v;
     }
+    MPC_PHASE_END
+    MPC_PHASE
     if (tid < NZ) {
         W[S::W_LB + tid] = L.lower_bound[tid];
         W[S::W_UB + tid] = L.upper_bound[tid];
@@ -990,7 +1014,6 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
             const int k = it / NZ, i = it - k * NZ;
             double *st = sm + k * S::STRIDE;
             if (!(k == N && i < NU)) st[S::Z + i] += st[S::DZ + i];
-            if (k >= 1 && i < NX) st[S::PI + i] = st[S::DPI + i];
             if (iterates) {
                 const double zi = st[S::Z + i];
                 if (k < N) iterates[(sq * (N + 1) + k) * NZ + i] = zi;
