@@ -53,16 +53,35 @@ __global__ void transpose_params_kernel(const double *__restrict__ params, doubl
     }
 }
 
+// Resident CTAs per SM the kernel is compiled for: what the shared-memory image allows (228 KB per SM, 1 KB
+// reserved per CTA), at most 4 (= 128 registers per thread).  Measured on B200 for the T-MPC stack (56 KB):
+// 2 / 3 / 4 CTAs per SM -> 197k / 245k / 271k solves/s.
 template <class CFG>
-__global__ void __launch_bounds__(MPC_NT) sqp_kernel(Layout L, int P, const double *__restrict__ xinit, const double *__restrict__ x0,
+constexpr int sqp_min_ctas() {
+    return (233472 / (int)(SL<CFG>::TOTAL * sizeof(double) + 1024)) >= 4   ? 4
+           : (233472 / (int)(SL<CFG>::TOTAL * sizeof(double) + 1024)) >= 1 ? (233472 / (int)(SL<CFG>::TOTAL * sizeof(double) + 1024))
+                                                                            : 1;
+}
+template <class CFG>
+__global__ void __launch_bounds__(MPC_NT, sqp_min_ctas<CFG>()) sqp_kernel(Layout L, int P, const double *__restrict__ xinit, const double *__restrict__ x0,
                                                  const double *__restrict__ pt, double *__restrict__ xtraj,
-                                                 double *__restrict__ utraj, mpcgpu_info *__restrict__ info) {
+                                                 double *__restrict__ utraj, mpcgpu_info *__restrict__ info,
+                                                 unsigned int *__restrict__ sm_slots) {
     extern __shared__ double sm[];
+    __shared__ int s_serial_tid;
     const int p = blockIdx.x;
     if (p >= P) return;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU;
+    // The serial Riccati sweeps run in ONE thread per CTA.  Warp w of every CTA lives on SM sub-partition w % 4, so
+    // co-resident CTAs would all serialise on sub-partition 0; a per-SM ticket spreads their serial warps round-robin.
+    if (threadIdx.x == 0) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_serial_tid = (int)((atomicAdd(&sm_slots[smid & 255], 1u) % (MPC_NT / 32)) * 32);
+    }
+    __syncthreads();
     sqp_solve_cta<CFG>(L, sm, xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt + (size_t)p * L.npar * 32,
-                        xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p, nullptr);
+                        xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p, nullptr, s_serial_tid);
 }
 
 // FindBestPlanner (mpc_planner_modules/src/guidance_constraints.cpp:416-434): per group of `group`
@@ -128,7 +147,7 @@ struct KernelTable {
     int smem_bytes;
     cudaError_t (*prepare)(int smem_bytes);
     void (*launch_sqp)(const Layout &, int P, const double *, const double *, const double *, double *, double *, mpcgpu_info *,
-                       int smem, cudaStream_t);
+                       unsigned int *, int smem, cudaStream_t);
     void (*launch_eval)(const Layout &, int M, const double *, const double *, const double *, const double *, double *, double *,
                         double *, double *, double *, double *, double *, double *, double *, cudaStream_t);
 };
@@ -139,8 +158,8 @@ cudaError_t prepare_cfg(int smem_bytes) {
 }
 template <class CFG>
 void launch_sqp_cfg(const Layout &L, int P, const double *xinit, const double *x0, const double *pt, double *xtraj, double *utraj,
-                    mpcgpu_info *info, int smem, cudaStream_t s) {
-    sqp_kernel<CFG><<<P, MPC_NT, smem, s>>>(L, P, xinit, x0, pt, xtraj, utraj, info);
+                    mpcgpu_info *info, unsigned int *sm_slots, int smem, cudaStream_t s) {
+    sqp_kernel<CFG><<<P, MPC_NT, smem, s>>>(L, P, xinit, x0, pt, xtraj, utraj, info, sm_slots);
 }
 template <class CFG>
 void launch_eval_cfg(const Layout &L, int M, const double *z, const double *p, const double *lam, const double *pi, double *cost,
@@ -173,6 +192,7 @@ struct mpcgpu_solver {
     double *d_xinit, *d_x0, *d_params, *d_pt, *d_xtraj, *d_utraj;
     mpcgpu_info *d_info;
     int *d_best;
+    unsigned int *d_sm_slots;  // per-SM tickets (see sqp_kernel)
     long long launches;
     int group;  // solves per selection group (0 = the whole batch)
     int timing;
@@ -246,6 +266,8 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     ok = ok && cudaMalloc(&h->d_utraj, B * h->n_utraj * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_info, B * sizeof(mpcgpu_info)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_best, B * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_sm_slots, 256 * sizeof(unsigned int)) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->d_sm_slots, 0, 256 * sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
     if (ok) ok = cudaMemset(h->d_pt, 0, B * (size_t)desc->npar * 32 * sizeof(double)) == cudaSuccess;
     if (!ok) {
@@ -268,6 +290,7 @@ int mpcgpu_destroy(mpcgpu_handle h) {
     cudaFree(h->d_utraj);
     cudaFree(h->d_info);
     cudaFree(h->d_best);
+    cudaFree(h->d_sm_slots);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -286,7 +309,7 @@ int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const dou
     if (tb > 148 * 16) tb = 148 * 16;
     transpose_params_kernel<<<tb, 256, 0, s>>>(d_params, h->d_pt, P, N, npar);
     if (h->timing) cudaEventRecord(h->ev0, s);
-    h->kt->launch_sqp(h->layout, P, d_xinit, d_x0, h->d_pt, d_xtraj, d_utraj, d_info, h->kt->smem_bytes, s);
+    h->kt->launch_sqp(h->layout, P, d_xinit, d_x0, h->d_pt, d_xtraj, d_utraj, d_info, h->d_sm_slots, h->kt->smem_bytes, s);
     if (h->timing) cudaEventRecord(h->ev1, s);
     h->launches += 2;
     if (d_best) {

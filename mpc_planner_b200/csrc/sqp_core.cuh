@@ -150,7 +150,8 @@ struct SL {
     static constexpr int W_DX0 = W_RED + 6 * MPC_RED_SLOTS;  // NX
     static constexpr int W_LB = W_DX0 + NX;     // NZ lower bounds (copy of Layout, for dynamic indexing)
     static constexpr int W_UB = W_LB + NZ;      // NZ upper bounds
-    static constexpr int W_PROF = W_UB + NZ;    // 32 doubles (profiling builds)
+    static constexpr int W_STID = W_UB + NZ;    // id of the thread that runs the serial Riccati sweeps
+    static constexpr int W_PROF = W_STID + 1;   // 32 doubles (profiling builds)
 #if defined(MPC_PROFILE)
     static constexpr int W_SIZE = W_PROF + 32;
 #else
@@ -307,7 +308,9 @@ MPC_HD void assemble_stage(const Layout &L, double *st) {
     double g[NZ];
 #pragma unroll
     for (int i = 0; i < NZ; i++) g[i] = st[S::LS_GC + i];
-    mirror_block<NZ>(Hp, L.reg_epsilon);
+    // Jacobi work space: M in the (dead between QPs) T/TINV/CORR rows area, V in the IPM work area
+    static_assert(3 * S::NROW >= NZ * NZ && S::RAW - S::WK >= NZ * NZ, "MIRROR work space");
+    mirror_block<NZ>(Hp, L.reg_epsilon, st + S::T, st + S::WK);
 #pragma unroll
     for (int i = 0; i < S::NHP; i++) st[S::H + i] = Hp[i];
 #pragma unroll
@@ -343,8 +346,9 @@ MPC_DEV void riccati_factor(double *sm) {
     typedef RicIdx<CFG> R;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
     static_assert(NU == 2, "input block is factorised in closed form for nu = 2");
+    const int serial_tid = (int)sm[S::W_BASE + S::W_STID];
     MPC_PHASE
-    if (tid == 0) {
+    if (tid == serial_tid) {
         double Pn[S::NPP];
 #pragma unroll
         for (int e = 0; e < S::NPP; e++) Pn[e] = sm[N * S::STRIDE + S::P + e];
@@ -454,8 +458,9 @@ MPC_DEV void riccati_solve(double *sm) {
     typedef RicIdx<CFG> R;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
     double *W = sm + S::W_BASE;
+    const int serial_tid = (int)W[S::W_STID];
     MPC_PHASE
-    if (tid == 0) {
+    if (tid == serial_tid) {
         // backward: m = gt + BA'(pv+ + P+ c);  y = Luu^-1 m_u;  pv = m_x - Lxu y
         double pv[NX];
 #pragma unroll
@@ -943,7 +948,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
 // ---------------------------------------------------------------------------------------------
 template <class CFG>
 MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, const double *x0, const double *pt,
-                           double *xtraj, double *utraj, mpcgpu_info *info, double *iterates) {
+                           double *xtraj, double *utraj, mpcgpu_info *info, double *iterates, int serial_tid = 0) {
     typedef SL<CFG> S;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NT = MPC_NT;
     static_assert(N + 1 <= 32, "parameters are staged in 32 columns");
@@ -977,6 +982,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         W[S::W_LB + tid] = L.lower_bound[tid];
         W[S::W_UB + tid] = L.upper_bound[tid];
     }
+    if (tid == NZ) W[S::W_STID] = (double)serial_tid;
     MPC_PHASE_END
 
     int qp_status = 0, sqp_iter = 0, qp_iter_total = 0;
