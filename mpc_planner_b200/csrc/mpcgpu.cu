@@ -187,7 +187,9 @@ struct mpcgpu_solver {
     Layout layout;
     const KernelTable *kt;
     int device, max_batch;
-    cudaStream_t stream;  // owned stream for the host path
+    cudaStream_t stream;  // owned streams for the host path: compute, H2D, D2H
+    cudaStream_t stream_in, stream_out;
+    cudaEvent_t ev_in[8], ev_cmp[8];
     // device buffers (host path)
     double *d_xinit, *d_x0, *d_params, *d_pt, *d_xtraj, *d_utraj;
     mpcgpu_info *d_info;
@@ -258,6 +260,11 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     const size_t B = (size_t)max_batch;
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; i++)
+        ok = cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_cmp[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_xinit, B * h->n_xinit * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_x0, B * h->n_x0 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_params, B * h->n_params * sizeof(double)) == cudaSuccess;
@@ -294,7 +301,35 @@ int mpcgpu_destroy(mpcgpu_handle h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream_in) cudaStreamDestroy(h->stream_in);
+    if (h->stream_out) cudaStreamDestroy(h->stream_out);
+    for (int i = 0; i < 8; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_cmp[i]) cudaEventDestroy(h->ev_cmp[i]);
+    }
     delete h;
+    return MPCGPU_OK;
+}
+
+// enqueue transpose -> sqp -> select_best for `count` solves whose scratch slot starts at `slot`
+static int enqueue_solve(mpcgpu_handle h, int slot, int count, const double *d_xinit, const double *d_x0, const double *d_params,
+                         double *d_xtraj, double *d_utraj, mpcgpu_info *d_info, int *d_best, cudaStream_t s, bool timed) {
+    const int N = h->desc.N, npar = h->desc.npar;
+    double *pt = h->d_pt + (size_t)slot * npar * 32;
+    const long long total = (long long)count * N * npar;
+    int tb = (int)((total + 255) / 256);
+    if (tb > 148 * 16) tb = 148 * 16;
+    transpose_params_kernel<<<tb, 256, 0, s>>>(d_params, pt, count, N, npar);
+    if (timed) cudaEventRecord(h->ev0, s);
+    h->kt->launch_sqp(h->layout, count, d_xinit, d_x0, pt, d_xtraj, d_utraj, d_info, h->d_sm_slots, h->kt->smem_bytes, s);
+    if (timed) cudaEventRecord(h->ev1, s);
+    h->launches += 2;
+    if (d_best) {
+        const int group = (h->group > 0) ? h->group : count, n_groups = (count + group - 1) / group;
+        select_best_kernel<<<(n_groups + 3) / 4, 128, 0, s>>>(d_info, count, group, n_groups, d_best);
+        h->launches += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
     return MPCGPU_OK;
 }
 
@@ -303,21 +338,8 @@ int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const dou
     if (!h || P <= 0 || !d_xinit || !d_x0 || !d_params || !d_xtraj || !d_utraj || !d_info) return MPCGPU_ERR_ARG;
     if (P > h->max_batch) return MPCGPU_ERR_BATCH;
     cudaStream_t s = (cudaStream_t)stream;
-    const int N = h->desc.N, npar = h->desc.npar;
-    const long long total = (long long)P * N * npar;
-    int tb = (int)((total + 255) / 256);
-    if (tb > 148 * 16) tb = 148 * 16;
-    transpose_params_kernel<<<tb, 256, 0, s>>>(d_params, h->d_pt, P, N, npar);
-    if (h->timing) cudaEventRecord(h->ev0, s);
-    h->kt->launch_sqp(h->layout, P, d_xinit, d_x0, h->d_pt, d_xtraj, d_utraj, d_info, h->d_sm_slots, h->kt->smem_bytes, s);
-    if (h->timing) cudaEventRecord(h->ev1, s);
-    h->launches += 2;
-    if (d_best) {
-        const int group = (h->group > 0) ? h->group : P, n_groups = (P + group - 1) / group;
-        select_best_kernel<<<(n_groups + 3) / 4, 128, 0, s>>>(d_info, P, group, n_groups, d_best);
-        h->launches += 1;
-    }
-    CUDA_TRY(cudaGetLastError());
+    int rc = enqueue_solve(h, 0, P, d_xinit, d_x0, d_params, d_xtraj, d_utraj, d_info, d_best, s, h->timing != 0);
+    if (rc != MPCGPU_OK) return rc;
     if (h->timing) {
         CUDA_TRY(cudaEventSynchronize(h->ev1));
         float ms = 0.f;
@@ -333,19 +355,37 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
     if (!h || P <= 0 || !xinit || !x0 || !params || !xtraj || !utraj || !info) return MPCGPU_ERR_ARG;
     if (P > h->max_batch) return MPCGPU_ERR_BATCH;
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
-    const size_t B = (size_t)P;
-    CUDA_TRY(cudaMemcpyAsync(h->d_xinit, xinit, B * h->n_xinit * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_x0, x0, B * h->n_x0 * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_params, params, B * h->n_params * sizeof(double), cudaMemcpyHostToDevice, s));
-    int rc = mpcgpu_solve_device(h, P, h->d_xinit, h->d_x0, h->d_params, h->d_xtraj, h->d_utraj, h->d_info, h->d_best, (void *)s);
-    if (rc != MPCGPU_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(xtraj, h->d_xtraj, B * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(utraj, h->d_utraj, B * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(info, h->d_info, B * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, s));
-    const int group = (h->group > 0) ? h->group : P, n_groups = (P + group - 1) / group;
-    if (best) CUDA_TRY(cudaMemcpyAsync(best, h->d_best, (size_t)n_groups * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    // Large batches are split into chunks pipelined over three streams (H2D | kernels | D2H) so that the PCIe
+    // copies of chunk i+1 / i-1 overlap the solve of chunk i.  Chunks are whole selection groups.
+    const int group = (h->group > 0) ? h->group : P;
+    int n_chunks = (P >= 2048 && h->group > 0) ? 8 : 1;
+    int chunk = (P + n_chunks - 1) / n_chunks;
+    chunk = ((chunk + group - 1) / group) * group;
+    n_chunks = (P + chunk - 1) / chunk;
+    for (int c = 0; c < n_chunks; c++) {
+        const size_t o = (size_t)c * chunk, n = (size_t)((o + chunk <= (size_t)P) ? chunk : P - o);
+        CUDA_TRY(cudaMemcpyAsync(h->d_xinit + o * h->n_xinit, xinit + o * h->n_xinit, n * h->n_xinit * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaMemcpyAsync(h->d_x0 + o * h->n_x0, x0 + o * h->n_x0, n * h->n_x0 * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaMemcpyAsync(h->d_params + o * h->n_params, params + o * h->n_params, n * h->n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[c], h->stream_in));
+    }
+    for (int c = 0; c < n_chunks; c++) {
+        const size_t o = (size_t)c * chunk, n = (size_t)((o + chunk <= (size_t)P) ? chunk : P - o);
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[c], 0));
+        int rc = enqueue_solve(h, (int)o, (int)n, h->d_xinit + o * h->n_xinit, h->d_x0 + o * h->n_x0, h->d_params + o * h->n_params,
+                               h->d_xtraj + o * h->n_xtraj, h->d_utraj + o * h->n_utraj, h->d_info + o, h->d_best + o / group, h->stream, false);
+        if (rc != MPCGPU_OK) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_cmp[c], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream_out, h->ev_cmp[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(xtraj + o * h->n_xtraj, h->d_xtraj + o * h->n_xtraj, n * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
+        CUDA_TRY(cudaMemcpyAsync(utraj + o * h->n_utraj, h->d_utraj + o * h->n_utraj, n * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
+        CUDA_TRY(cudaMemcpyAsync(info + o, h->d_info + o, n * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, h->stream_out));
+        if (best) {
+            const size_t ng = (n + group - 1) / group;
+            CUDA_TRY(cudaMemcpyAsync(best + o / group, h->d_best + o / group, ng * sizeof(int), cudaMemcpyDeviceToHost, h->stream_out));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream_out));
     return MPCGPU_OK;
 }
 

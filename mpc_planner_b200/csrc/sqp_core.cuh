@@ -955,13 +955,6 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     double *W = sm + S::W_BASE;
     double *mpc_prof = W + S::W_PROF;
     (void)mpc_prof;
-#if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 32; i++) mpc_prof[i] = 0.0;
-        mpc_prof[31] = (double)clock64();
-    }
-    __syncthreads();
-#endif
     // loadWarmstart (acados_solver_interface.cpp:274-284): x (k = 0..N) and u (k < N) from x0;
     // fresh solver: zero multipliers
     MPC_PHASE
@@ -984,6 +977,13 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     }
     if (tid == NZ) W[S::W_STID] = (double)serial_tid;
     MPC_PHASE_END
+#if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 32; i++) mpc_prof[i] = 0.0;
+        mpc_prof[31] = (double)clock64();
+    }
+    __syncthreads();
+#endif
 
     int qp_status = 0, sqp_iter = 0, qp_iter_total = 0;
     double qp_res[2] = {0.0, 0.0};  // last QP: stationarity / complementarity residuals
