@@ -188,7 +188,7 @@ struct mpcgpu_solver {
     const KernelTable *kt;
     int device, max_batch;
     cudaStream_t stream;  // owned streams for the host path: compute, H2D, D2H
-    cudaStream_t stream_in, stream_out;
+    cudaStream_t stream_in, stream_out, stream2;  // stream2: second compute stream (chunk kernels overlap their tails)
     cudaEvent_t ev_in[8], ev_cmp[8];
     // device buffers (host path)
     double *d_xinit, *d_x0, *d_params, *d_pt, *d_xtraj, *d_utraj;
@@ -262,6 +262,7 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 8 && ok; i++)
         ok = cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_cmp[i], cudaEventDisableTiming) == cudaSuccess;
@@ -303,6 +304,7 @@ int mpcgpu_destroy(mpcgpu_handle h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream_in) cudaStreamDestroy(h->stream_in);
     if (h->stream_out) cudaStreamDestroy(h->stream_out);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     for (int i = 0; i < 8; i++) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_cmp[i]) cudaEventDestroy(h->ev_cmp[i]);
@@ -358,7 +360,7 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
     // Large batches are split into chunks pipelined over three streams (H2D | kernels | D2H) so that the PCIe
     // copies of chunk i+1 / i-1 overlap the solve of chunk i.  Chunks are whole selection groups.
     const int group = (h->group > 0) ? h->group : P;
-    int n_chunks = (P >= 2048 && h->group > 0) ? 8 : 1;
+    int n_chunks = (P >= 2048 && h->group > 0) ? 4 : 1;
     int chunk = (P + n_chunks - 1) / n_chunks;
     chunk = ((chunk + group - 1) / group) * group;
     n_chunks = (P + chunk - 1) / chunk;
@@ -371,11 +373,13 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
     }
     for (int c = 0; c < n_chunks; c++) {
         const size_t o = (size_t)c * chunk, n = (size_t)((o + chunk <= (size_t)P) ? chunk : P - o);
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[c], 0));
+        cudaStream_t sc = (c & 1) ? h->stream2 : h->stream;  // alternate compute streams: the partial last wave of one
+                                                              // chunk overlaps the first wave of the next
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
         int rc = enqueue_solve(h, (int)o, (int)n, h->d_xinit + o * h->n_xinit, h->d_x0 + o * h->n_x0, h->d_params + o * h->n_params,
-                               h->d_xtraj + o * h->n_xtraj, h->d_utraj + o * h->n_utraj, h->d_info + o, h->d_best + o / group, h->stream, false);
+                               h->d_xtraj + o * h->n_xtraj, h->d_utraj + o * h->n_utraj, h->d_info + o, h->d_best + o / group, sc, false);
         if (rc != MPCGPU_OK) return rc;
-        CUDA_TRY(cudaEventRecord(h->ev_cmp[c], h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev_cmp[c], sc));
         CUDA_TRY(cudaStreamWaitEvent(h->stream_out, h->ev_cmp[c], 0));
         CUDA_TRY(cudaMemcpyAsync(xtraj + o * h->n_xtraj, h->d_xtraj + o * h->n_xtraj, n * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
         CUDA_TRY(cudaMemcpyAsync(utraj + o * h->n_utraj, h->d_utraj + o * h->n_utraj, n * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
