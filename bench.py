@@ -391,6 +391,12 @@ def main():
             v, threads, n_cpu, dt = cpu_arm(spec, target_seconds=float(os.environ.get("MPC_BENCH_CPU_SECONDS", "12")))
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{n_cpu} solves of the same workload in {dt:.1f} s, OpenMP over the batch ({threads} threads of {usable_cores()} usable CPUs); acados-equivalent CPU restatement (oracle/), not acados"}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one sqp_kernel launch (ncu --set full)
+            tj = json.load(open(tpath))
+            if tj.get("grid") == P:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -402,7 +408,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "sqp_kernel", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SOLVE * P, "peak_source": peak_src, "kernel": "sqp_kernel", "kernel_ms": kernel_ms,
                          "note": "latency/FP64-issue bound by design (SURVEY.md 8d); see fp64"},
             "fp64": {"achieved": achieved_gflops, "peak": fp64_peak, "unit": "GFLOP/s", "frac": achieved_gflops / fp64_peak if fp64_peak > 0 else None,
                      "flops_per_solve": fl, "peak_source": "measured in this run (dependent-free DFMA chains, all SMs)"},
