@@ -310,7 +310,12 @@ MPC_HD void assemble_stage(const Layout &L, double *st) {
     for (int i = 0; i < NZ; i++) g[i] = st[S::LS_GC + i];
     // Jacobi work space: M in the (dead between QPs) T/TINV/CORR rows area, V in the IPM work area
     static_assert(3 * S::NROW >= NZ * NZ && S::RAW - S::WK >= NZ * NZ, "MIRROR work space");
-    mirror_block<NZ>(Hp, L.reg_epsilon, st + S::T, st + S::WK);
+    // block structure of the MPCC Hessian: {a, w, psi, v} and {x, y, spline (, slack)} decouple unless the disc is
+    // offset from the robot centre (then d2h/dx dpsi != 0) -- checked at run time inside mirror_block
+    constexpr bool BLOCKS = (CFG::OBJ == MPCGPU_OBJ_CONTOURING);
+    const int ia[4] = {CFG::IA, CFG::IW, CFG::IPSI, CFG::IV};
+    const int ib[4] = {CFG::IX, CFG::IY, CFG::IS, CFG::HAS_SLACK ? CFG::ISLACK : 0};
+    mirror_block<NZ, (BLOCKS ? 4 : 0)>(Hp, L.reg_epsilon, st + S::T, st + S::WK, ia, ib);
 #pragma unroll
     for (int i = 0; i < S::NHP; i++) st[S::H + i] = Hp[i];
 #pragma unroll
