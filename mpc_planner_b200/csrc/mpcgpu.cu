@@ -377,7 +377,7 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
                                                               // chunk overlaps the first wave of the next
         CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
         int rc = enqueue_solve(h, (int)o, (int)n, h->d_xinit + o * h->n_xinit, h->d_x0 + o * h->n_x0, h->d_params + o * h->n_params,
-                               h->d_xtraj + o * h->n_xtraj, h->d_utraj + o * h->n_utraj, h->d_info + o, h->d_best + o / group, sc, false);
+                               h->d_xtraj + o * h->n_xtraj, h->d_utraj + o * h->n_utraj, h->d_info + o, h->d_best + o / group, sc, h->timing != 0 && n_chunks == 1);
         if (rc != MPCGPU_OK) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_cmp[c], sc));
         CUDA_TRY(cudaStreamWaitEvent(h->stream_out, h->ev_cmp[c], 0));
@@ -390,6 +390,12 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
         }
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream_out));
+    if (h->timing && n_chunks == 1) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->ms_acc += ms;
+        h->ms_n += 1;
+    }
     return MPCGPU_OK;
 }
 
