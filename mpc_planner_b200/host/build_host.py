@@ -20,3 +20,17 @@ def build_test(name="cfg2", out_dir=None):
            "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-o", exe]
     subprocess.check_call(cmd)
     return exe
+
+
+def build_modules_test(name="cfg2", out_dir=None):
+    """The module layer (parameter packing + batched T-MPC++ loop) and its test driver."""
+    spec = pb.CONFIGS[name]()
+    out_dir = out_dir or os.path.join(HERE, "generated", name)
+    generate_solver(spec, out_dir)
+    exe = os.path.join(out_dir, "test_modules")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I" + out_dir, "-I" + os.path.join(HERE, "include"), "-I" + os.path.join(libbuild.ROOT, "include"),
+           os.path.join(HERE, "src", "cuda_solver_interface.cpp"), os.path.join(HERE, "src", "modules.cpp"),
+           os.path.join(HERE, "test", "test_modules.cpp"), "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-o", exe]
+    subprocess.check_call(cmd)
+    return exe

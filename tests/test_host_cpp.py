@@ -68,3 +68,155 @@ def test_cpp_solver_matches_python_binding(exe, tmp_path):
         assert pobj == info[i]["pobj"]  # same kernel, same inputs: bit-identical
         np.testing.assert_array_equal(cx, xt[i].ravel())
         np.testing.assert_array_equal(cu, ut[i].ravel())
+
+
+# ---------------------------------------------------------------------------------------------
+# module layer: parameter packing (MPCBase / Contouring / Ellipsoid / Linearized) + batched T-MPC++ loop
+# ---------------------------------------------------------------------------------------------
+def _make_scene(tmp_path, consistency=1.0, selected=-1):
+    from mpc_planner_b200.scenes import _fit_path, _path_eval
+
+    spec = pb.config_tmpc()
+    N, dt = spec.N, spec.dt
+    coef, starts = _fit_path(1.2, 6, phase=0.4)  # 6 segments: the module picks 5 starting at the closest one
+    s0 = 1.0
+    p0, d0 = _path_eval(coef, starts, s0)
+    state = dict(x=p0[0], y=p0[1] + 0.1, psi=float(np.arctan2(d0[1], d0[0])), v=1.5, spline=0.0)
+    t = dt * np.arange(N + 1)
+    base_s = s0 + 2.0 * t
+    base, der = _path_eval(coef, starts, base_s)
+    head = np.arctan2(der[:, 1], der[:, 0])
+    nrm = np.stack([-np.sin(head), np.cos(head)], 1)
+    # 8 obstacle slots (ensureObstacleSize pads to max_obstacles): 3 real ones + far-away dummies
+    obs = np.zeros((8, N, 2))  # prediction step j = position at time (j+1) dt
+    for o in range(8):
+        if o < 3:
+            start = base[6 + 3 * o] + (0.3 - 0.3 * o) * nrm[6 + 3 * o]
+            vel = np.array([-0.3, 0.2 * (o - 1)])
+            obs[o] = start[None] + (t[1:, None] - t[6 + 3 * o]) * vel[None]
+        else:
+            obs[o] = np.array([state["x"] + 100.0 + o, state["y"] + 100.0])[None]
+    guid = []
+    for side in (+1.0, -1.0):
+        lat = side * 1.3 * np.clip(t / 1.0, 0, 1)
+        pos = base + lat[:, None] * nrm
+        vel = np.gradient(pos, dt, axis=0)
+        guid.append((pos, vel))
+    f = tmp_path / "scene.bin"
+    vals = [state[k] for k in ("x", "y", "psi", "v", "spline")] + [6]
+    for i in range(6):
+        vals += list(coef[i, 0]) + list(coef[i, 1]) + [starts[i]]
+    vals += [30.0, 8, N]
+    for o in range(8):
+        vals += list(obs[o].ravel())
+    vals += [len(guid), N + 1]
+    for g, (pos, vel) in enumerate(guid):
+        vals += [1.0 if g == selected else 0.0] + list(pos.ravel()) + list(vel.ravel())
+    vals += [consistency]
+    np.array(vals, dtype=np.float64).tofile(f)
+    return spec, f, state, coef, starts, obs, guid
+
+
+def _read_modules_output(path, spec):
+    raw = np.fromfile(path, dtype=np.float64)
+    n, exit_code, best = int(raw[0]), int(raw[1]), int(raw[2])
+    off, planners = 3, []
+    sz = spec.sizes()
+    for _ in range(n):
+        d = dict(id=int(raw[off]), original=bool(raw[off + 1]))
+        off += 2
+        for key in ("xinit", "x0", "params"):
+            d[key] = raw[off:off + sz[key]].copy()
+            off += sz[key]
+        d["exit_code"], d["objective"] = int(raw[off]), raw[off + 1]
+        off += 2
+        d["xtraj"] = raw[off:off + sz["xtraj"]].copy()
+        off += sz["xtraj"]
+        d["utraj"] = raw[off:off + sz["utraj"]].copy()
+        off += sz["utraj"]
+        planners.append(d)
+    main_xtraj = raw[off:off + sz["xtraj"]].copy()
+    main_pobj = raw[off + sz["xtraj"]]
+    return exit_code, best, planners, main_xtraj, main_pobj
+
+
+@pytest.fixture(scope="module")
+def modules_exe():
+    return build_host.build_modules_test("cfg2")
+
+
+def test_module_parameter_packing_follows_the_reference(modules_exe, tmp_path):
+    spec, scene, state, coef, starts, obs, guid = _make_scene(tmp_path)
+    out = tmp_path / "out.bin"
+    r = subprocess.run([modules_exe, "pack", str(scene), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    _, _, planners, _, _ = _read_modules_output(out, spec)
+    assert [p["id"] for p in planners] == [0, 1, 2] and [p["original"] for p in planners] == [False, False, True]
+    pm, N, npar, nz, nu = spec.parameter_map(), spec.N, spec.npar, spec.nz, spec.nu
+    from mpc_planner_b200.scenes import WEIGHTS, ROBOT_RADIUS, OBSTACLE_RADIUS
+
+    for p in planners:
+        par = p["params"].reshape(N, npar)
+        x0 = p["x0"].reshape(N + 1, nz)
+        # Contouring::update put the closest point into the state / xinit (contouring.cpp:37,42)
+        assert abs(p["xinit"][4] - 1.0) < 0.05  # closest-point search on a 1 cm grid; the state is 0.1 m off the path
+        for k in range(N):
+            for w in ("acceleration", "angular_velocity", "velocity", "reference_velocity", "contour", "lag"):  # mpc_base.cpp:23-35
+                assert par[k, pm[w]] == WEIGHTS[w]
+            for i in range(5):  # contouring.cpp:94-124: the same 5 segments at every stage, from the closest one (0)
+                np.testing.assert_array_equal(par[k, pm[f"spline_x{i}_a"]:pm[f"spline_x{i}_a"] + 4], coef[i, 0])
+                np.testing.assert_array_equal(par[k, pm[f"spline_y{i}_a"]:pm[f"spline_y{i}_a"] + 4], coef[i, 1])
+                assert par[k, pm[f"spline{i}_start"]] == starts[i]
+            assert par[k, pm["ego_disc_radius"]] == ROBOT_RADIUS and par[k, pm["ego_disc_0_offset"]] == 0.0
+            for o in range(8):  # ellipsoid_constraints.cpp:34-90
+                e = {s: par[k, pm[f"ellipsoid_obst_{o}_{s}"]] for s in ("x", "y", "psi", "major", "minor", "chi", "r")}
+                if k == 0:
+                    assert (e["x"], e["y"], e["r"], e["chi"]) == (state["x"] + 50, state["y"] + 50, 0.1, 1.0)
+                else:  # prediction step k-1 feeds stage k
+                    assert (e["x"], e["y"]) == tuple(obs[o, k - 1]) and e["r"] == OBSTACLE_RADIUS and e["chi"] == 1.0 and e["major"] == 0.0
+                a1, a2, b = (par[k, pm[f"lin_constraint_{o}_{s}"]] for s in ("a1", "a2", "b"))
+                if k == 0 or p["original"]:  # linearized_constraints.cpp:155-166, guidance_constraints.cpp:301-305
+                    assert (a1, a2, b) == (1.0, 0.0, state["x"] + 100.0)
+                else:  # :85-105, topology mode: r = 1e-3
+                    gp = guid[p["id"]][0][k]
+                    dvec = obs[o, k - 1] - gp
+                    a = dvec / np.linalg.norm(dvec)
+                    np.testing.assert_allclose([a1, a2, b], [a[0], a[1], a @ obs[o, k - 1] - (1e-3 + ROBOT_RADIUS)], rtol=1e-12)
+        if not p["original"]:  # guidance warm start k = 1..N-1 (guidance_constraints.cpp:401-413)
+            pos, vel = guid[p["id"]]
+            for k in range(1, N):
+                np.testing.assert_allclose(x0[k, nu:nu + 2], pos[k], rtol=1e-14)
+                assert x0[k, nu + 2] == pytest.approx(np.arctan2(vel[k, 1], vel[k, 0]))
+                assert x0[k, nu + 3] == pytest.approx(np.linalg.norm(vel[k]))
+        else:  # braking plan of the main solver (acados_solver_interface.cpp:303-342)
+            assert x0[1, nu + 3] == pytest.approx(1.5 - 3.0 * spec.dt) and x0[3, 0] == -3.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("selected,consistency", [(-1, 1.0), (1, 1e-3)])
+def test_batched_tmpc_loop_matches_oracle(modules_exe, tmp_path, selected, consistency):
+    from oracle import oracle
+
+    spec, scene, *_ = _make_scene(tmp_path, consistency=consistency, selected=selected)
+    out = tmp_path / "out.bin"
+    r = subprocess.run([modules_exe, "gpu", str(scene), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exit_code, best, planners, main_xtraj, main_pobj = _read_modules_output(out, spec)
+    xi = np.array([p["xinit"] for p in planners])
+    x0 = np.array([p["x0"] for p in planners])
+    par = np.array([p["params"] for p in planners])
+    oxt, out_, oinfo = oracle.solve_batch(spec, xi, x0, par)
+    objs = []
+    for i, p in enumerate(planners):
+        assert p["exit_code"] == oinfo[i]["exit_code"]
+        w = consistency if (p["id"] == selected and not p["original"]) else 1.0
+        if oinfo[i]["exit_code"] == 1:
+            np.testing.assert_allclose(p["xtraj"], oxt[i].ravel(), rtol=1e-6, atol=1e-6)
+            assert p["objective"] == pytest.approx(oinfo[i]["pobj"] * w, rel=1e-6)
+            objs.append((oinfo[i]["pobj"] * w, i))
+    assert objs, "at least one planner must be feasible in this scene"
+    want = min(objs)[1]
+    assert best == want and exit_code == 1
+    np.testing.assert_array_equal(main_xtraj, planners[best]["xtraj"])  # guidance_constraints.cpp:382-384
+    if selected >= 0:
+        assert best == selected  # the consistency weight makes the previously selected guess win (:358-359)
