@@ -1067,6 +1067,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         int exit_code = 1;
         if (qp_status == 3 || qp_status == 4) exit_code = 4;  // ACADOS_QP_FAILURE
         if (!(res_eq <= L.res_eq_fail) && exit_code == 1) exit_code = 4;  // acados_solver_interface.cpp:176-181
+        if (!(pobj == pobj) || isinf(pobj)) exit_code = 4;               // a non-finite objective is never a success
         info->pobj = pobj;
         info->res_eq = res_eq;
         info->res_stat_qp = qp_res[0];
