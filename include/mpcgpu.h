@@ -147,6 +147,22 @@ int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const dou
                         const double *d_params, double *d_xtraj, double *d_utraj,
                         mpcgpu_info *d_info, int *d_best, void *stream);
 
+/* T-MPC++ control steps with DEVICE-SIDE construction of the topology halfspaces and parameter packing.
+ * Replaces, for S control steps x G guesses each, the per-planner work of GuidanceConstraints::optimize before
+ * solve(): `*local_solver = *_solver` (guidance_constraints.cpp:298) and LinearizedConstraints::update /
+ * projectToSafety / setParameters in topology mode (linearized_constraints.cpp:49-189).
+ *   xinit[S*nx], x0[S*G*(nu+nx)*(N+1)] (the guesses' warm starts = guidance trajectories),
+ *   scene_params[S*N*npar]: the MAIN solver's parameters of each control step (weights, spline, obstacle
+ *       predictions; the lin_constraint slots are ignored) -- uploaded once per step, not once per guess;
+ *   guided[G]: 1 = guided planner (halfspaces a = (o - p)/|o - p|, b = a.o - (1e-3 + robot_radius) from its warm
+ *       start p_k, after projecting p_k out of the obstacle discs), 0 = non-guided planner (dummy halfspaces
+ *       (1, 0, x0 + 100) everywhere); stage 0 always gets the dummies.
+ * Needs a problem with a LINEAR block followed by an ELLIPSOID or GAUSSIAN block.  Outputs as
+ * mpcgpu_solve_host with P = S*G; best[S] is the winner within each control step. */
+int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, const double *x0,
+                           const double *scene_params, const int *guided, double robot_radius, double *xtraj,
+                           double *utraj, mpcgpu_info *info, int *best);
+
 /* Selection groups: consecutive blocks of `group` solves are the guesses of one control step;
  * `best` / `d_best` then receive ceil(P/group) entries, each the within-group index of the winner
  * (or -1).  group = 0 (default) treats the whole batch as one group. */

@@ -20,7 +20,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 # every symbol include/mpcgpu.h declares
 EXPORTED_SYMBOLS = [
     "mpcgpu_version", "mpcgpu_strerror", "mpcgpu_device_count", "mpcgpu_problem_supported", "mpcgpu_create", "mpcgpu_destroy",
-    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_set_group", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
+    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_set_group", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
     "mpcgpu_set_timing", "mpcgpu_kernel_ms", "mpcgpu_eval_stage", "mpcgpu_measure_fp64_gflops",
 ]
 
@@ -46,6 +46,8 @@ def load_library():
     lib.mpcgpu_destroy.argtypes = [ctypes.c_void_p]
     lib.mpcgpu_solve_host.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, ctypes.POINTER(SolveInfo), _ip]
     lib.mpcgpu_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 8
+    lib.mpcgpu_solve_tmpc_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, _ip, ctypes.c_double, _dp, _dp,
+                                           ctypes.POINTER(SolveInfo), _ip]
     lib.mpcgpu_set_group.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.mpcgpu_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_ulonglong]
     lib.mpcgpu_host_free.argtypes = [ctypes.c_void_p]
@@ -127,6 +129,26 @@ class BatchSolver:
         _check(self.lib.mpcgpu_solve_host(self.handle, P, _p(xinit), _p(x0), _p(params), _p(xtraj), _p(utraj), info,
                                           best.ctypes.data_as(_ip)), "mpcgpu_solve_host")
         return xtraj, utraj, infos_to_dicts(info), (int(best[0]) if self.group == 0 else best)
+
+    # ---- T-MPC++ control steps with device-side halfspace construction and parameter packing ----
+    def solve_tmpc(self, xinit, x0, scene_params, guided, robot_radius=0.325):
+        """S control steps x G guesses.  xinit [S,nx], x0 [S*G, ...] (guess-minor), scene_params [S, N*npar] (the main
+        solver's parameters per step), guided [G] flags.  Returns (xtraj, utraj, infos, best[S])."""
+        s = self.spec
+        xinit = np.ascontiguousarray(xinit, float).reshape(-1, s.nx)
+        S = xinit.shape[0]
+        guided = np.ascontiguousarray(guided, np.int32)
+        G = len(guided)
+        P = S * G
+        x0 = np.ascontiguousarray(x0, float).reshape(P, s.nz * (s.N + 1))
+        scene_params = np.ascontiguousarray(scene_params, float).reshape(S, s.npar * s.N)
+        xtraj, utraj = np.empty((P, s.N + 1, s.nx)), np.empty((P, s.N, s.nu))
+        info = (SolveInfo * P)()
+        best = np.full(S, -1, dtype=np.int32)
+        _check(self.lib.mpcgpu_solve_tmpc_host(self.handle, S, G, _p(xinit), _p(x0), _p(scene_params), guided.ctypes.data_as(_ip),
+                                               float(robot_radius), _p(xtraj), _p(utraj), info, best.ctypes.data_as(_ip)),
+               "mpcgpu_solve_tmpc_host")
+        return xtraj, utraj, infos_to_dicts(info), best
 
     # ---- device-buffer path (raw pointers, e.g. torch tensors' data_ptr()) ----
     def solve_device(self, P, d_xinit, d_x0, d_params, d_xtraj, d_utraj, d_info, d_best=None, stream=None):

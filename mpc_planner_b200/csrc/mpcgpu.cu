@@ -56,6 +56,59 @@ __global__ void transpose_params_kernel(const double *__restrict__ params, doubl
 // Resident CTAs per SM the kernel is compiled for: what the shared-memory image allows (228 KB per SM, 1 KB
 // reserved per CTA), at most 4 (= 128 registers per thread).  Measured on B200 for the T-MPC stack (56 KB):
 // 2 / 3 / 4 CTAs per SM -> 197k / 245k / 271k solves/s.
+// T-MPC++: per (control step s, guess g) build the solve's transposed parameter block from the step's main-solver
+// parameters and, for guided guesses, the topology halfspaces from the guess's warm start
+// (LinearizedConstraints::update / projectToSafety / setParameters, linearized_constraints.cpp:49-189).
+__global__ void pack_tmpc_kernel(const double *__restrict__ scene_params, const double *__restrict__ xinit_scene,
+                                 const double *__restrict__ x0, const int *__restrict__ guided, double *__restrict__ pt,
+                                 double *__restrict__ xinit_out, int S, int G, int N, int npar, int nx, int nu, int lin0, int n_lin,
+                                 int obs0, int obs_stride, int n_obs, double robot_radius) {
+    const int p = blockIdx.x, s = p / G, g = p - s * G;
+    if (s >= S) return;
+    const double *sp = scene_params + (size_t)s * N * npar;
+    double *ptp = pt + (size_t)p * npar * 32;
+    for (int idx = threadIdx.x; idx < N * npar; idx += blockDim.x) {
+        const int k = idx / npar, i = idx - k * npar;
+        ptp[i * 32 + k] = sp[idx];
+    }
+    if (threadIdx.x < nx) xinit_out[(size_t)p * nx + threadIdx.x] = xinit_scene[(size_t)s * nx + threadIdx.x];
+    __syncthreads();
+    const int nz = nx + nu;
+    const double x_init = xinit_scene[(size_t)s * nx];
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const bool build = (guided[g] != 0) && (k >= 1);
+        double px = 0.0, py = 0.0;
+        const double R = 1e-3 + robot_radius;  // topology mode: obstacle radius 1e-3 (linearized_constraints.cpp:101)
+        if (build) {
+            px = x0[((size_t)p * (N + 1) + k) * nz + nu];
+            py = x0[((size_t)p * (N + 1) + k) * nz + nu + 1];
+            for (int sweep = 0; sweep < 3; sweep++)  // projectToSafety: at most 3 sweeps (stand-in for Douglas-Rachford)
+                for (int o = 0; o < n_obs; o++) {
+                    const double ox = sp[k * npar + obs0 + obs_stride * o], oy = sp[k * npar + obs0 + obs_stride * o + 1];
+                    double dx = px - ox, dy = py - oy, dist = sqrt(dx * dx + dy * dy);
+                    if (dist < R) {
+                        if (dist < 1e-9) { dx = 1.0; dy = 0.0; dist = 1.0; }
+                        px = ox + dx / dist * R;
+                        py = oy + dy / dist * R;
+                    }
+                }
+        }
+        for (int j = 0; j < n_lin; j++) {
+            double a1 = 1.0, a2 = 0.0, b = x_init + 100.0;  // dummies (linearized_constraints.cpp:53,155-166,181-187)
+            if (build && j < n_obs) {
+                const double ox = sp[k * npar + obs0 + obs_stride * j], oy = sp[k * npar + obs0 + obs_stride * j + 1];
+                const double dx = ox - px, dy = oy - py, dist = sqrt(dx * dx + dy * dy);
+                a1 = dx / dist;
+                a2 = dy / dist;
+                b = a1 * ox + a2 * oy - R;
+            }
+            ptp[(lin0 + 3 * j) * 32 + k] = a1;
+            ptp[(lin0 + 3 * j + 1) * 32 + k] = a2;
+            ptp[(lin0 + 3 * j + 2) * 32 + k] = b;
+        }
+    }
+}
+
 template <class CFG>
 constexpr int sqp_min_ctas() {
     return (233472 / (int)(SL<CFG>::TOTAL * sizeof(double) + 1024)) >= 4   ? 4
@@ -195,6 +248,7 @@ struct mpcgpu_solver {
     mpcgpu_info *d_info;
     int *d_best;
     unsigned int *d_sm_slots;  // per-SM tickets (see sqp_kernel)
+    int *d_guided;             // T-MPC guided flags (lazy)
     long long launches;
     int group;  // solves per selection group (0 = the whole batch)
     int timing;
@@ -299,6 +353,7 @@ int mpcgpu_destroy(mpcgpu_handle h) {
     cudaFree(h->d_info);
     cudaFree(h->d_best);
     cudaFree(h->d_sm_slots);
+    cudaFree(h->d_guided);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -406,6 +461,51 @@ int mpcgpu_host_alloc(void **ptr, unsigned long long bytes) {
 }
 int mpcgpu_host_free(void *ptr) {
     CUDA_TRY(cudaFreeHost(ptr));
+    return MPCGPU_OK;
+}
+
+int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, const double *x0, const double *scene_params,
+                           const int *guided, double robot_radius, double *xtraj, double *utraj, mpcgpu_info *info, int *best) {
+    if (!h || S <= 0 || G <= 0 || !xinit || !x0 || !scene_params || !guided || !xtraj || !utraj || !info) return MPCGPU_ERR_ARG;
+    const int P = S * G;
+    if (P > h->max_batch) return MPCGPU_ERR_BATCH;
+    const mpcgpu_problem_desc &d = h->desc;
+    int m_lin = -1, m_obs = -1;
+    for (int m = 0; m < d.n_con_modules; m++) {
+        if (d.con_kind[m] == MPCGPU_CON_LINEAR && m_lin < 0) m_lin = m;
+        if ((d.con_kind[m] == MPCGPU_CON_ELLIPSOID || d.con_kind[m] == MPCGPU_CON_GAUSSIAN) && m_obs < 0) m_obs = m;
+    }
+    if (m_lin < 0 || m_obs < 0) return MPCGPU_ERR_UNSUPPORTED;
+    const int obs_stride = (d.con_kind[m_obs] == MPCGPU_CON_ELLIPSOID) ? 7 : 6;
+    const int n_obs = d.con_count[m_lin] < d.con_count[m_obs] ? d.con_count[m_lin] : d.con_count[m_obs];
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    if (!h->d_guided) CUDA_TRY(cudaMalloc(&h->d_guided, 1024 * sizeof(int)));
+    if (G > 1024) return MPCGPU_ERR_ARG;
+    // scene parameters are staged in d_params (S blocks <= P blocks), scene xinit behind the expanded one
+    CUDA_TRY(cudaMemcpyAsync(h->d_params, scene_params, (size_t)S * h->n_params * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_x0, x0, (size_t)P * h->n_x0 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_xtraj, xinit, (size_t)S * h->n_xinit * sizeof(double), cudaMemcpyHostToDevice, s));  // scratch
+    CUDA_TRY(cudaMemcpyAsync(h->d_guided, guided, (size_t)G * sizeof(int), cudaMemcpyHostToDevice, s));
+    pack_tmpc_kernel<<<P, 128, 0, s>>>(h->d_params, h->d_xtraj, h->d_x0, h->d_guided, h->d_pt, h->d_xinit, S, G, d.N, d.npar, d.nx, d.nu,
+                                       d.con_param[m_lin], d.con_count[m_lin], d.con_param[m_obs], obs_stride, n_obs, robot_radius);
+    if (h->timing) cudaEventRecord(h->ev0, s);
+    h->kt->launch_sqp(h->layout, P, h->d_xinit, h->d_x0, h->d_pt, h->d_xtraj, h->d_utraj, h->d_info, h->d_sm_slots, h->kt->smem_bytes, s);
+    if (h->timing) cudaEventRecord(h->ev1, s);
+    select_best_kernel<<<(S + 3) / 4, 128, 0, s>>>(h->d_info, P, G, S, h->d_best);
+    h->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(xtraj, h->d_xtraj, (size_t)P * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(utraj, h->d_utraj, (size_t)P * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(info, h->d_info, (size_t)P * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, s));
+    if (best) CUDA_TRY(cudaMemcpyAsync(best, h->d_best, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (h->timing) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->ms_acc += ms;
+        h->ms_n += 1;
+    }
     return MPCGPU_OK;
 }
 

@@ -78,3 +78,25 @@ def test_solve_matches_oracle(binding, name, scenes_guesses):
     assert n_ok >= max(1, (S * P) // 3)
     assert solver.launches >= 3
     solver.close()
+
+
+def test_device_side_topology_constraints_match_host_packing(binding):
+    """mpcgpu_solve_tmpc_host builds the topology halfspaces and the per-guess parameter blocks on the device
+    (LinearizedConstraints::update / setParameters, linearized_constraints.cpp:49-189); the result must equal the
+    host-packed path on the same scenes."""
+    spec = SPECS["cfg2"]
+    S, G = 6, 8
+    b = scenes.make_scene_batch(spec, S, G, seed=41)
+    solver = binding.BatchSolver(spec, S * G)
+    solver.set_group(G)
+    xt, ut, info, best = solver.solve(b["xinit"], b["x0"], b["params"])
+    scene_params = b["params"].reshape(S, G, -1)[:, 0]  # the non-guided planner's block = the main solver's parameters
+    guided = np.array([0] + [1] * (G - 1), dtype=np.int32)
+    xt2, ut2, info2, best2 = solver.solve_tmpc(b["xinit"].reshape(S, G, -1)[:, 0], b["x0"], scene_params, guided,
+                                               robot_radius=scenes.ROBOT_RADIUS)
+    assert [i["exit_code"] for i in info] == [i["exit_code"] for i in info2]
+    ok = np.array([i["exit_code"] == 1 for i in info])
+    np.testing.assert_allclose(xt2[ok], xt[ok], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose([i["pobj"] for i, o in zip(info2, ok) if o], [i["pobj"] for i, o in zip(info, ok) if o], rtol=1e-7)
+    np.testing.assert_array_equal(best2, best)
+    solver.close()
