@@ -249,6 +249,7 @@ struct mpcgpu_solver {
     int *d_best;
     unsigned int *d_sm_slots;  // per-SM tickets (see sqp_kernel)
     int *d_guided;             // T-MPC guided flags (lazy)
+    double *d_xinit_scene;     // T-MPC per-control-step initial states (lazy)
     long long launches;
     int group;  // solves per selection group (0 = the whole batch)
     int timing;
@@ -354,6 +355,7 @@ int mpcgpu_destroy(mpcgpu_handle h) {
     cudaFree(h->d_best);
     cudaFree(h->d_sm_slots);
     cudaFree(h->d_guided);
+    cudaFree(h->d_xinit_scene);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -478,29 +480,49 @@ int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, c
     if (m_lin < 0 || m_obs < 0) return MPCGPU_ERR_UNSUPPORTED;
     const int obs_stride = (d.con_kind[m_obs] == MPCGPU_CON_ELLIPSOID) ? 7 : 6;
     const int n_obs = d.con_count[m_lin] < d.con_count[m_obs] ? d.con_count[m_lin] : d.con_count[m_obs];
-    CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
-    if (!h->d_guided) CUDA_TRY(cudaMalloc(&h->d_guided, 1024 * sizeof(int)));
     if (G > 1024) return MPCGPU_ERR_ARG;
-    // scene parameters are staged in d_params (S blocks <= P blocks), scene xinit behind the expanded one
-    CUDA_TRY(cudaMemcpyAsync(h->d_params, scene_params, (size_t)S * h->n_params * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_x0, x0, (size_t)P * h->n_x0 * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_xtraj, xinit, (size_t)S * h->n_xinit * sizeof(double), cudaMemcpyHostToDevice, s));  // scratch
-    CUDA_TRY(cudaMemcpyAsync(h->d_guided, guided, (size_t)G * sizeof(int), cudaMemcpyHostToDevice, s));
-    pack_tmpc_kernel<<<P, 128, 0, s>>>(h->d_params, h->d_xtraj, h->d_x0, h->d_guided, h->d_pt, h->d_xinit, S, G, d.N, d.npar, d.nx, d.nu,
-                                       d.con_param[m_lin], d.con_count[m_lin], d.con_param[m_obs], obs_stride, n_obs, robot_radius);
-    if (h->timing) cudaEventRecord(h->ev0, s);
-    h->kt->launch_sqp(h->layout, P, h->d_xinit, h->d_x0, h->d_pt, h->d_xtraj, h->d_utraj, h->d_info, h->d_sm_slots, h->kt->smem_bytes, s);
-    if (h->timing) cudaEventRecord(h->ev1, s);
-    select_best_kernel<<<(S + 3) / 4, 128, 0, s>>>(h->d_info, P, G, S, h->d_best);
-    h->launches += 3;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(xtraj, h->d_xtraj, (size_t)P * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(utraj, h->d_utraj, (size_t)P * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(info, h->d_info, (size_t)P * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, s));
-    if (best) CUDA_TRY(cudaMemcpyAsync(best, h->d_best, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (h->timing) {
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->d_guided) {
+        CUDA_TRY(cudaMalloc(&h->d_guided, 1024 * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_xinit_scene, (size_t)h->max_batch * h->n_xinit * sizeof(double)));
+    }
+    // Chunks of whole control steps, pipelined like mpcgpu_solve_host (H2D | two compute streams | D2H).
+    int n_chunks = (P >= 2048) ? 4 : 1;
+    int sc_chunk = (S + n_chunks - 1) / n_chunks;
+    n_chunks = (S + sc_chunk - 1) / sc_chunk;
+    CUDA_TRY(cudaMemcpyAsync(h->d_guided, guided, (size_t)G * sizeof(int), cudaMemcpyHostToDevice, h->stream_in));
+    for (int c = 0; c < n_chunks; c++) {
+        const size_t s0 = (size_t)c * sc_chunk, ns = (s0 + sc_chunk <= (size_t)S) ? sc_chunk : S - s0, p0 = s0 * G, np = ns * G;
+        // the control steps' parameter blocks are staged in d_params (S blocks <= P blocks)
+        CUDA_TRY(cudaMemcpyAsync(h->d_params + s0 * h->n_params, scene_params + s0 * h->n_params, ns * h->n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaMemcpyAsync(h->d_x0 + p0 * h->n_x0, x0 + p0 * h->n_x0, np * h->n_x0 * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaMemcpyAsync(h->d_xinit_scene + s0 * h->n_xinit, xinit + s0 * h->n_xinit, ns * h->n_xinit * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[c], h->stream_in));
+    }
+    for (int c = 0; c < n_chunks; c++) {
+        const size_t s0 = (size_t)c * sc_chunk, ns = (s0 + sc_chunk <= (size_t)S) ? sc_chunk : S - s0, p0 = s0 * G, np = ns * G;
+        cudaStream_t sc = (c & 1) ? h->stream2 : h->stream;
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
+        pack_tmpc_kernel<<<(unsigned)np, 128, 0, sc>>>(h->d_params + s0 * h->n_params, h->d_xinit_scene + s0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_guided,
+                                                       h->d_pt + p0 * (size_t)d.npar * 32, h->d_xinit + p0 * h->n_xinit, (int)ns, G, d.N, d.npar, d.nx, d.nu,
+                                                       d.con_param[m_lin], d.con_count[m_lin], d.con_param[m_obs], obs_stride, n_obs, robot_radius);
+        const bool timed = h->timing != 0 && n_chunks == 1;
+        if (timed) cudaEventRecord(h->ev0, sc);
+        h->kt->launch_sqp(h->layout, (int)np, h->d_xinit + p0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_pt + p0 * (size_t)d.npar * 32,
+                          h->d_xtraj + p0 * h->n_xtraj, h->d_utraj + p0 * h->n_utraj, h->d_info + p0, h->d_sm_slots, h->kt->smem_bytes, sc);
+        if (timed) cudaEventRecord(h->ev1, sc);
+        select_best_kernel<<<(unsigned)((ns + 3) / 4), 128, 0, sc>>>(h->d_info + p0, (int)np, G, (int)ns, h->d_best + s0);
+        h->launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(h->ev_cmp[c], sc));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream_out, h->ev_cmp[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(xtraj + p0 * h->n_xtraj, h->d_xtraj + p0 * h->n_xtraj, np * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
+        CUDA_TRY(cudaMemcpyAsync(utraj + p0 * h->n_utraj, h->d_utraj + p0 * h->n_utraj, np * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
+        CUDA_TRY(cudaMemcpyAsync(info + p0, h->d_info + p0, np * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, h->stream_out));
+        if (best) CUDA_TRY(cudaMemcpyAsync(best + s0, h->d_best + s0, ns * sizeof(int), cudaMemcpyDeviceToHost, h->stream_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream_out));
+    if (h->timing && n_chunks == 1) {
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         h->ms_acc += ms;
