@@ -13,7 +13,7 @@ from .problem import ProblemDesc, ProblemSpec, SolveInfo
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmpcgpu.so")
-_lib = None
+_libs = {}
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
 
@@ -29,14 +29,15 @@ class MpcGpuError(RuntimeError):
     pass
 
 
-def load_library():
-    """dlopen the CUDA library (never builds, never falls back)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise MpcGpuError(f"{LIB_PATH} is missing: build it with `python -m mpc_planner_b200.build` (there is no CPU fallback)")
-    lib = ctypes.CDLL(LIB_PATH)
+def load_library(path: str | None = None):
+    """dlopen the CUDA library (never builds, never falls back).  `path` selects a per-problem library emitted by
+    `generate.build_solver_library`; the default is the in-tree library with the shipped module stacks."""
+    path = os.path.abspath(path or LIB_PATH)
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise MpcGpuError(f"{path} is missing: build it with `python -m mpc_planner_b200.build` (there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
     lib.mpcgpu_version.restype = ctypes.c_char_p
     lib.mpcgpu_strerror.restype = ctypes.c_char_p
     lib.mpcgpu_strerror.argtypes = [ctypes.c_int]
@@ -59,7 +60,7 @@ def load_library():
     lib.mpcgpu_eval_stage.argtypes = [ctypes.c_void_p, ctypes.c_int] + [_dp] * 13
     lib.mpcgpu_measure_fp64_gflops.restype = ctypes.c_double
     lib.mpcgpu_measure_fp64_gflops.argtypes = [ctypes.c_int]
-    _lib = lib
+    _libs[path] = lib
     return lib
 
 
@@ -85,8 +86,8 @@ assert INFO_DTYPE.itemsize == ctypes.sizeof(SolveInfo)
 class BatchSolver:
     """P simultaneous `Solver::solve()` calls on one GPU (mpcgpu_create / mpcgpu_solve_*)."""
 
-    def __init__(self, spec: ProblemSpec, max_batch: int, device: int = 0):
-        self.lib = load_library()
+    def __init__(self, spec: ProblemSpec, max_batch: int, device: int = 0, library: str | None = None):
+        self.lib = load_library(library)
         self.spec = spec
         self.desc = spec.desc()
         self.max_batch = int(max_batch)

@@ -35,15 +35,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, output=None, registry_header=None):
+    """Compile the library.  With `registry_header` (a file emitted by generate.generate_cuda_registry) the kernels
+    are instantiated for that module stack only and the result is written to `output`."""
+    out = output or LIB
+    if output is None and not force and not needs_build():
         return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I" + os.path.join(ROOT, "include"), "-o", LIB] + [
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    extra = []
+    if registry_header is not None:
+        extra = ["-DMPCGPU_GENERATED_REGISTRY=\"%s\"" % os.path.abspath(registry_header)]
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-I" + os.path.join(ROOT, "include"), "-o", out] + [
         os.path.join(CSRC, s) for s in SOURCES
     ]
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -8,6 +8,12 @@
 
 namespace mpcgpu {
 
+#ifdef MPCGPU_GENERATED_REGISTRY
+// A per-problem library: `python -m mpc_planner_b200.generate --build` emits a header with the Config<> typedef(s) of
+// ONE module stack and its own MPCGPU_CONFIG_LIST, and compiles this translation unit against it
+// (the analogue of generate_acados_solver.py producing one solver library per stack).
+#include MPCGPU_GENERATED_REGISTRY
+#else
 // cfg 1: MPCBase + Contouring + Ellipsoid(4)   generate_jackalsimulator_solver.py:61-66
 typedef Config<MPCGPU_MODEL_UNICYCLE, MPCGPU_OBJ_CONTOURING, 20, 5, MPCGPU_CON_ELLIPSOID, 4> cfg_basic_n20_o4;
 // cfg 2/5: T-MPC: Guidance(linear 8 + Ellipsoid 8)   :94-103
@@ -28,6 +34,8 @@ typedef Config<MPCGPU_MODEL_UNICYCLE_SLACK, MPCGPU_OBJ_CONTOURING, 20, 5, MPCGPU
     X(cfg_tmpc_n30_o12)       \
     X(cfg_tmpc_decomp_n30_o12) \
     X(cfg_safe_horizon_n20)
+
+#endif  // MPCGPU_GENERATED_REGISTRY
 
 template <class CFG>
 inline bool config_matches(const mpcgpu_problem_desc &d) {

@@ -12,6 +12,14 @@ _lib = None
 _dp = ctypes.POINTER(ctypes.c_double)
 
 
+def build_generated(registry_header, out):
+    """Host emulation of a GENERATED kernel instantiation (generate.generate_cuda_registry)."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include"),
+                           '-DMPCGPU_GENERATED_REGISTRY="%s"' % os.path.abspath(registry_header), "-o", out, os.path.join(_HERE, "emu.cpp")])
+    return out
+
+
 def build(force=False):
     srcs = [os.path.join(_HERE, "emu.cpp")] + [
         os.path.join(_ROOT, "mpc_planner_b200", "csrc", f) for f in ("sqp_core.cuh", "stage_functions.cuh", "registry.cuh")
@@ -53,7 +61,7 @@ def eval_stage(desc, z, p, lam=None, pi=None):
     return out
 
 
-def solve_batch(spec, xinit, x0, params, iterates=False):
+def solve_batch(spec, xinit, x0, params, iterates=False, library=None):
     from mpc_planner_b200.problem import SolveInfo
 
     desc = spec.desc()
@@ -65,7 +73,7 @@ def solve_batch(spec, xinit, x0, params, iterates=False):
     xtraj, utraj = np.zeros((P, N + 1, nx)), np.zeros((P, N, nu))
     info = (SolveInfo * P)()
     its = np.zeros((P, spec.n_sqp, N + 1, nz)) if iterates else None
-    rc = lib().emu_solve(ctypes.byref(desc), P, _p(xinit), _p(x0), _p(params), _p(xtraj), _p(utraj), info, _p(its))
+    rc = (ctypes.CDLL(library) if library else lib()).emu_solve(ctypes.byref(desc), P, _p(xinit), _p(x0), _p(params), _p(xtraj), _p(utraj), info, _p(its))
     if rc != 0:
         raise RuntimeError(f"emu_solve: {rc}")
     infos = [dict(pobj=i.pobj, res_eq=i.res_eq, res_stat_qp=i.res_stat_qp, res_comp_qp=i.res_comp_qp, exit_code=i.exit_code,
