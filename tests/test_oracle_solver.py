@@ -110,3 +110,85 @@ def test_mirror_regularisation():
         got = np.ascontiguousarray(A.copy())
         oracle.lib().oracle_mirror(n, got.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_double(eps))
         np.testing.assert_allclose(got, want, atol=1e-12)
+
+
+def test_first_rti_step_solves_the_qp_an_independent_solver_finds():
+    """QP level (assembly + Mehrotra IPM + Riccati): with zero multipliers the first SQP-RTI step is
+    z0 + argmin of the QP built from the stage linearisations at z0 (MIRROR-regularised dt-scaled cost Hessian,
+    linearised ERK4 dynamics, boxes, linearised h).  The QP is convex, so scipy's SLSQP -- which shares no code with
+    the oracle's interior-point method -- must return the same step up to the IPM's tolerance (qp_tol = 1e-5)."""
+    import ctypes
+
+    from scipy.optimize import minimize
+
+    spec = pb.config_tmpc()
+    b = scenes.make_scene_batch(spec, 1, 3, seed=4)
+    d = spec.desc()
+    N, nx, nu, nz, npar = spec.N, spec.nx, spec.nu, spec.nz, spec.npar
+    xt, ut, info, its = oracle.solve_batch(spec, b["xinit"], b["x0"], b["params"], iterates=True)
+    lh, uh = map(np.array, spec.constraint_bounds())
+    lo, up = np.array(list(d.lower_bound)[:nz]), np.array(list(d.upper_bound)[:nz])
+    checked = 0
+    for i in range(len(info)):
+        if info[i]["exit_code"] != 1:
+            continue
+        par = b["params"][i].reshape(N, npar)
+        z0 = b["x0"][i].reshape(N + 1, nz)
+        xN0 = z0[N, nu:]  # warm start of node N: [u (unused); x]
+        ev = [oracle.eval_stage(d, z0[k], par[k]) for k in range(N)]
+        H = []
+        for k in range(N):
+            Hk = np.ascontiguousarray(spec.dt * ev[k]["cost_hess"])
+            oracle.lib().oracle_mirror(nz, Hk.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_double(spec.reg_epsilon))
+            H.append(Hk)
+        g = [spec.dt * ev[k]["cost_grad"] for k in range(N)]
+        nvar = N * nz + nx
+
+        def split(w):
+            return w[: N * nz].reshape(N, nz), w[N * nz:]
+
+        def obj(w):
+            dz, dxN = split(w)
+            return sum(0.5 * dz[k] @ H[k] @ dz[k] + g[k] @ dz[k] for k in range(N)) + 0.5 * spec.reg_epsilon * dxN @ dxN
+
+        def obj_grad(w):
+            dz, dxN = split(w)
+            return np.concatenate([np.concatenate([H[k] @ dz[k] + g[k] for k in range(N)]), spec.reg_epsilon * dxN])
+
+        def eq(w):
+            dz, dxN = split(w)
+            out = [z0[0, nu:] + dz[0, nu:] - b["xinit"][i]]
+            for k in range(N):
+                nxt = (z0[k + 1, nu:] + dz[k + 1, nu:]) if k + 1 < N else (xN0 + dxN)
+                out.append(ev[k]["xnext"] + ev[k]["AB"] @ dz[k] - nxt)
+            return np.concatenate(out)
+
+        def ineq(w):
+            dz, _ = split(w)
+            out = []
+            for k in range(N):
+                sl = slice(0, nz) if k >= 1 else slice(0, nu)
+                out += [z0[k, sl] + dz[k, sl] - lo[sl], up[sl] - z0[k, sl] - dz[k, sl]]
+                if k >= 1:
+                    h = ev[k]["h"] + ev[k]["h_jac"] @ dz[k]
+                    out += [(h - lh)[np.isfinite(lh)], (uh - h)[np.isfinite(uh)]]
+            return np.concatenate(out)
+
+        # start SLSQP from zero (NOT from the oracle's step)
+        res = minimize(obj, np.zeros(nvar), jac=obj_grad, method="SLSQP", constraints=[dict(type="eq", fun=eq), dict(type="ineq", fun=ineq)],
+                       options=dict(maxiter=400, ftol=1e-14))
+        assert res.success, res.message
+        dz_ref, dxN_ref = split(res.x)
+        step = its[i, 0, :N] - z0[:N]
+        stepN = its[i, 0, N, :nx] - xN0
+        w_or = np.concatenate([step.ravel(), stepN])
+        assert np.abs(eq(w_or)).max() < 1e-8 and ineq(w_or).min() > -1e-8  # the oracle's step is QP-feasible
+        assert obj(w_or) == pytest.approx(res.fun, abs=2e-5)  # complementarity <= qp_tol per row
+        assert obj(w_or) >= res.fun - 1e-7
+        np.testing.assert_allclose(step, dz_ref, atol=5e-4)
+        np.testing.assert_allclose(stepN, dxN_ref, atol=5e-4)
+        print('qp check: obj gap', obj(w_or) - res.fun, 'max step diff', np.abs(step - dz_ref).max())
+        checked += 1
+        if checked >= 2:
+            break
+    assert checked >= 1
