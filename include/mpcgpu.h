@@ -163,6 +163,18 @@ int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, c
                            const double *scene_params, const int *guided, double robot_radius, double *xtraj,
                            double *utraj, mpcgpu_info *info, int *best);
 
+/* Persistent NLP multipliers ("stateful" solver slots).  In the reference every LocalPlanner owns a Solver whose
+ * acados memory survives `*local_solver = *_solver` (operator= copies parameters only,
+ * acados_solver_interface.cpp:67-77): the multipliers of its previous solve enter the first exact Hessian of the next
+ * control step.  With mpcgpu_set_stateful(h, 1) solve slot p (the p-th problem of every solve call on this handle)
+ * keeps [pi (N+1) x nx | multipliers of h, N x nh] (mpcgpu_state_size doubles) in HBM between calls; a QP failure
+ * clears the slot, as does mpcgpu_reset_state (Solver::reset, :79-84).  get/set copy slots to/from host memory. */
+int mpcgpu_set_stateful(mpcgpu_handle h, int enable);
+int mpcgpu_state_size(mpcgpu_handle h);
+int mpcgpu_reset_state(mpcgpu_handle h, int first, int count);
+int mpcgpu_get_state(mpcgpu_handle h, int first, int count, double *state);
+int mpcgpu_set_state(mpcgpu_handle h, int first, int count, const double *state);
+
 /* Selection groups: consecutive blocks of `group` solves are the guesses of one control step;
  * `best` / `d_best` then receive ceil(P/group) entries, each the within-group index of the winner
  * (or -1).  group = 0 (default) treats the whole batch as one group. */

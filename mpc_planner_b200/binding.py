@@ -20,7 +20,8 @@ _ip = ctypes.POINTER(ctypes.c_int)
 # every symbol include/mpcgpu.h declares
 EXPORTED_SYMBOLS = [
     "mpcgpu_version", "mpcgpu_strerror", "mpcgpu_device_count", "mpcgpu_problem_supported", "mpcgpu_create", "mpcgpu_destroy",
-    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_set_group", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
+    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_set_group",
+    "mpcgpu_set_stateful", "mpcgpu_state_size", "mpcgpu_reset_state", "mpcgpu_get_state", "mpcgpu_set_state", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
     "mpcgpu_set_timing", "mpcgpu_kernel_ms", "mpcgpu_eval_stage", "mpcgpu_measure_fp64_gflops",
 ]
 
@@ -50,6 +51,11 @@ def load_library(path: str | None = None):
     lib.mpcgpu_solve_tmpc_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, _ip, ctypes.c_double, _dp, _dp,
                                            ctypes.POINTER(SolveInfo), _ip]
     lib.mpcgpu_set_group.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.mpcgpu_set_stateful.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.mpcgpu_state_size.argtypes = [ctypes.c_void_p]
+    lib.mpcgpu_reset_state.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.mpcgpu_get_state.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp]
+    lib.mpcgpu_set_state.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp]
     lib.mpcgpu_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_ulonglong]
     lib.mpcgpu_host_free.argtypes = [ctypes.c_void_p]
     lib.mpcgpu_launch_count.restype = ctypes.c_longlong
@@ -103,6 +109,26 @@ class BatchSolver:
         """Guesses per control step: `best` becomes one winner index per group of consecutive solves."""
         _check(self.lib.mpcgpu_set_group(self.handle, int(group)), "mpcgpu_set_group")
         self.group = int(group)
+
+    # ---- persistent NLP multipliers per solve slot (Solver::operator= keeps the destination's acados memory) ----
+    def set_stateful(self, enable=True):
+        _check(self.lib.mpcgpu_set_stateful(self.handle, int(bool(enable))), "mpcgpu_set_stateful")
+
+    def state_size(self):
+        return int(self.lib.mpcgpu_state_size(self.handle))
+
+    def reset_state(self, first=0, count=None):
+        _check(self.lib.mpcgpu_reset_state(self.handle, int(first), int(self.max_batch - first if count is None else count)), "mpcgpu_reset_state")
+
+    def get_state(self, first=0, count=None):
+        count = self.max_batch - first if count is None else count
+        out = np.empty((count, self.state_size()))
+        _check(self.lib.mpcgpu_get_state(self.handle, int(first), int(count), _p(out)), "mpcgpu_get_state")
+        return out
+
+    def set_state(self, state, first=0):
+        state = np.ascontiguousarray(state, float).reshape(-1, self.state_size())
+        _check(self.lib.mpcgpu_set_state(self.handle, int(first), int(state.shape[0]), _p(state)), "mpcgpu_set_state")
 
     def close(self):
         if getattr(self, "handle", None):

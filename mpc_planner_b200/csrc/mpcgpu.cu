@@ -119,7 +119,7 @@ template <class CFG>
 __global__ void __launch_bounds__(MPC_NT, sqp_min_ctas<CFG>()) sqp_kernel(Layout L, int P, const double *__restrict__ xinit, const double *__restrict__ x0,
                                                  const double *__restrict__ pt, double *__restrict__ xtraj,
                                                  double *__restrict__ utraj, mpcgpu_info *__restrict__ info,
-                                                 unsigned int *__restrict__ sm_slots) {
+                                                 unsigned int *__restrict__ sm_slots, double *__restrict__ state) {
     extern __shared__ double sm[];
     __shared__ int s_serial_tid;
     const int p = blockIdx.x;
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(MPC_NT, sqp_min_ctas<CFG>()) sqp_kernel(Layout
     }
     __syncthreads();
     sqp_solve_cta<CFG>(L, sm, xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt + (size_t)p * L.npar * 32,
-                        xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p, nullptr, s_serial_tid);
+                        xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p, nullptr,
+                        state ? state + (size_t)p * ((N + 1) * NX + N * CFG::NH) : nullptr, s_serial_tid);
 }
 
 // FindBestPlanner (mpc_planner_modules/src/guidance_constraints.cpp:416-434): per group of `group`
@@ -200,7 +201,7 @@ struct KernelTable {
     int smem_bytes;
     cudaError_t (*prepare)(int smem_bytes);
     void (*launch_sqp)(const Layout &, int P, const double *, const double *, const double *, double *, double *, mpcgpu_info *,
-                       unsigned int *, int smem, cudaStream_t);
+                       unsigned int *, double *state, int smem, cudaStream_t);
     void (*launch_eval)(const Layout &, int M, const double *, const double *, const double *, const double *, double *, double *,
                         double *, double *, double *, double *, double *, double *, double *, cudaStream_t);
 };
@@ -211,8 +212,8 @@ cudaError_t prepare_cfg(int smem_bytes) {
 }
 template <class CFG>
 void launch_sqp_cfg(const Layout &L, int P, const double *xinit, const double *x0, const double *pt, double *xtraj, double *utraj,
-                    mpcgpu_info *info, unsigned int *sm_slots, int smem, cudaStream_t s) {
-    sqp_kernel<CFG><<<P, MPC_NT, smem, s>>>(L, P, xinit, x0, pt, xtraj, utraj, info, sm_slots);
+                    mpcgpu_info *info, unsigned int *sm_slots, double *state, int smem, cudaStream_t s) {
+    sqp_kernel<CFG><<<P, MPC_NT, smem, s>>>(L, P, xinit, x0, pt, xtraj, utraj, info, sm_slots, state);
 }
 template <class CFG>
 void launch_eval_cfg(const Layout &L, int M, const double *z, const double *p, const double *lam, const double *pi, double *cost,
@@ -248,6 +249,8 @@ struct mpcgpu_solver {
     mpcgpu_info *d_info;
     int *d_best;
     unsigned int *d_sm_slots;  // per-SM tickets (see sqp_kernel)
+    double *d_state;           // persistent NLP multipliers per solve slot (mpcgpu_set_stateful), else null
+    size_t n_state;
     int *d_guided;             // T-MPC guided flags (lazy)
     double *d_xinit_scene;     // T-MPC per-control-step initial states (lazy)
     long long launches;
@@ -306,6 +309,7 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     h->n_params = (size_t)desc->npar * N;
     h->n_xtraj = (size_t)nx * (N + 1);
     h->n_utraj = (size_t)nu * N;
+    h->n_state = (size_t)(N + 1) * nx + (size_t)N * desc->nh;
     cudaError_t e = kt->prepare(kt->smem_bytes);
     if (e != cudaSuccess) {
         snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cudaFuncSetAttribute(smem=%d): %s", kt->smem_bytes, cudaGetErrorString(e));
@@ -354,6 +358,7 @@ int mpcgpu_destroy(mpcgpu_handle h) {
     cudaFree(h->d_info);
     cudaFree(h->d_best);
     cudaFree(h->d_sm_slots);
+    cudaFree(h->d_state);
     cudaFree(h->d_guided);
     cudaFree(h->d_xinit_scene);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -380,7 +385,8 @@ static int enqueue_solve(mpcgpu_handle h, int slot, int count, const double *d_x
     if (tb > 148 * 16) tb = 148 * 16;
     transpose_params_kernel<<<tb, 256, 0, s>>>(d_params, pt, count, N, npar);
     if (timed) cudaEventRecord(h->ev0, s);
-    h->kt->launch_sqp(h->layout, count, d_xinit, d_x0, pt, d_xtraj, d_utraj, d_info, h->d_sm_slots, h->kt->smem_bytes, s);
+    h->kt->launch_sqp(h->layout, count, d_xinit, d_x0, pt, d_xtraj, d_utraj, d_info, h->d_sm_slots,
+                      h->d_state ? h->d_state + (size_t)slot * h->n_state : nullptr, h->kt->smem_bytes, s);
     if (timed) cudaEventRecord(h->ev1, s);
     h->launches += 2;
     if (d_best) {
@@ -509,7 +515,8 @@ int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, c
         const bool timed = h->timing != 0 && n_chunks == 1;
         if (timed) cudaEventRecord(h->ev0, sc);
         h->kt->launch_sqp(h->layout, (int)np, h->d_xinit + p0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_pt + p0 * (size_t)d.npar * 32,
-                          h->d_xtraj + p0 * h->n_xtraj, h->d_utraj + p0 * h->n_utraj, h->d_info + p0, h->d_sm_slots, h->kt->smem_bytes, sc);
+                          h->d_xtraj + p0 * h->n_xtraj, h->d_utraj + p0 * h->n_utraj, h->d_info + p0, h->d_sm_slots,
+                          h->d_state ? h->d_state + p0 * h->n_state : nullptr, h->kt->smem_bytes, sc);
         if (timed) cudaEventRecord(h->ev1, sc);
         select_best_kernel<<<(unsigned)((ns + 3) / 4), 128, 0, sc>>>(h->d_info + p0, (int)np, G, (int)ns, h->d_best + s0);
         h->launches += 3;
@@ -528,6 +535,45 @@ int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, c
         h->ms_acc += ms;
         h->ms_n += 1;
     }
+    return MPCGPU_OK;
+}
+
+int mpcgpu_state_size(mpcgpu_handle h) { return h ? (int)h->n_state : 0; }
+
+int mpcgpu_set_stateful(mpcgpu_handle h, int enable) {
+    if (!h) return MPCGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (enable && !h->d_state) {
+        CUDA_TRY(cudaMalloc(&h->d_state, (size_t)h->max_batch * h->n_state * sizeof(double)));
+        CUDA_TRY(cudaMemset(h->d_state, 0, (size_t)h->max_batch * h->n_state * sizeof(double)));
+    } else if (!enable && h->d_state) {
+        CUDA_TRY(cudaFree(h->d_state));
+        h->d_state = nullptr;
+    }
+    return MPCGPU_OK;
+}
+
+static int state_range_ok(mpcgpu_handle h, int first, int count) {
+    return h && h->d_state && first >= 0 && count >= 0 && first + count <= h->max_batch;
+}
+int mpcgpu_reset_state(mpcgpu_handle h, int first, int count) {
+    if (!state_range_ok(h, first, count)) return MPCGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemsetAsync(h->d_state + (size_t)first * h->n_state, 0, (size_t)count * h->n_state * sizeof(double), h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MPCGPU_OK;
+}
+int mpcgpu_get_state(mpcgpu_handle h, int first, int count, double *state) {
+    if (!state_range_ok(h, first, count) || !state) return MPCGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpy(state, h->d_state + (size_t)first * h->n_state, (size_t)count * h->n_state * sizeof(double), cudaMemcpyDeviceToHost));
+    return MPCGPU_OK;
+}
+int mpcgpu_set_state(mpcgpu_handle h, int first, int count, const double *state) {
+    if (!state_range_ok(h, first, count) || !state) return MPCGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpy(h->d_state + (size_t)first * h->n_state, state, (size_t)count * h->n_state * sizeof(double), cudaMemcpyHostToDevice));
     return MPCGPU_OK;
 }
 

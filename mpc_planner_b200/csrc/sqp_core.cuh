@@ -953,15 +953,18 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
 // ---------------------------------------------------------------------------------------------
 template <class CFG>
 MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, const double *x0, const double *pt,
-                           double *xtraj, double *utraj, mpcgpu_info *info, double *iterates, int serial_tid = 0) {
+                           double *xtraj, double *utraj, mpcgpu_info *info, double *iterates, double *state = nullptr,
+                           int serial_tid = 0) {
     typedef SL<CFG> S;
-    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NT = MPC_NT;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NT = MPC_NT;
     static_assert(N + 1 <= 32, "parameters are staged in 32 columns");
     double *W = sm + S::W_BASE;
     double *mpc_prof = W + S::W_PROF;
     (void)mpc_prof;
     // loadWarmstart (acados_solver_interface.cpp:274-284): x (k = 0..N) and u (k < N) from x0;
-    // fresh solver: zero multipliers
+    // fresh solver: zero multipliers.  With `state` ([pi (N+1) x NX | h multipliers N x NH], mpcgpu_set_stateful) the
+    // NLP multipliers of this solver slot's previous solve enter the first exact Hessian, as they do in a reference
+    // local solver whose acados memory survives `operator=` (acados_solver_interface.cpp:67-77).
     MPC_PHASE
     for (int it = tid; it < (N + 1) * S::STRIDE; it += NT) {
         const int k = it / S::STRIDE, o = it - k * S::STRIDE;
@@ -971,6 +974,10 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
             int i = 0;
             while ((i + 1) * (i + 2) / 2 <= o - S::P) i++;
             if (o - S::P == tri(i, i)) v = L.reg_epsilon;
+        }
+        if (state) {
+            if (o >= S::PI && o < S::PI + NX) v = state[k * NX + (o - S::PI)];
+            if (NH > 0 && k < N && o >= S::LAM + 2 * NZ && o < S::LAM + 2 * NZ + NH) v = state[(N + 1) * NX + k * NH + (o - S::LAM - 2 * NZ)];
         }
         sm[it] = v;
     }
@@ -1038,6 +1045,18 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
 
     // completeOneIteration (acados_solver_interface.cpp:162-204): cost, trajectories, res_eq
     MPC_PHASE
+    if (state) {  // persist the NLP multipliers; a QP failure clears them, non-finite values are never persisted
+        const bool keep = !(qp_status == 3 || qp_status == 4);
+        for (int it = tid; it < (N + 1) * NX; it += NT) {
+            const double v = sm[(it / NX) * S::STRIDE + S::PI + it % NX];
+            state[it] = (keep && isfinite(v)) ? v : 0.0;
+        }
+        if (NH > 0)
+            for (int it = tid; it < N * NH; it += NT) {
+                const double v = sm[(it / NH) * S::STRIDE + S::LAM + 2 * NZ + it % NH];
+                state[(N + 1) * NX + it] = (keep && isfinite(v)) ? v : 0.0;
+            }
+    }
     {
         double c = 0.0, defect = 0.0;
         if (tid < N) {

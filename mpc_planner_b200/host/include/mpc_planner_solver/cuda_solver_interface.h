@@ -97,7 +97,15 @@ class Solver {
      *  exit_codes receives each solver's exit code. */
     static int solveBatch(const std::vector<Solver *> &solvers, std::vector<int> &exit_codes);
 
+    /** The NLP multipliers of this solver's previous solve ([pi | multipliers of h], mpcgpu_state_size doubles).
+     *  They belong to the Solver object like acados' nlp_out does: kept by operator= (:67-77), cleared by reset()
+     *  (:79-84), fed to the first exact Hessian of the next solve.  Set persistent_multipliers = false for a solver
+     *  that starts every solve from zero multipliers. */
+    static bool persistent_multipliers;
+    const std::vector<double> &nlpMultipliers() const { return _nlp_multipliers; }
+
   private:
+    std::vector<double> _nlp_multipliers;
     mpcgpu_problem_desc _desc;
     mpcgpu_handle _handle{nullptr};  // created lazily: constructing a Solver needs no GPU
     std::vector<double> _loaded_x0;  // snapshot taken by loadWarmstart()

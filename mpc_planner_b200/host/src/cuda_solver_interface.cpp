@@ -46,6 +46,8 @@ Solver::Solver(int solver_id)  // :9-49
     reset();
 }
 
+bool Solver::persistent_multipliers = true;
+
 Solver::~Solver() {
     if (_handle) mpcgpu_destroy(_handle);
 }
@@ -60,6 +62,7 @@ void Solver::reset() {  // :79-84
     _info = Info();
     _output = Output();
     _loaded_x0 = _params.x0;
+    _nlp_multipliers.assign((size_t)(_desc.N + 1) * _desc.nx + (size_t)_desc.N * _desc.nh, 0.0);
 }
 
 mpcgpu_handle Solver::handle(int max_batch) {
@@ -69,6 +72,8 @@ mpcgpu_handle Solver::handle(int max_batch) {
     int rc = mpcgpu_create(&_desc, 0, max_batch, &_handle);
     if (rc != 0) throw std::runtime_error(std::string("mpcgpu_create: ") + mpcgpu_strerror(rc));
     _handle_batch = max_batch;
+    rc = mpcgpu_set_stateful(_handle, 1);
+    if (rc != 0) throw std::runtime_error(std::string("mpcgpu_set_stateful: ") + mpcgpu_strerror(rc));
     return _handle;
 }
 
@@ -97,10 +102,13 @@ int Solver::solveOneIteration() {  // :145-160
     if (_iteration_done) return _exit_code_one_iter == 1 ? 0 : _exit_code_one_iter;
     mpcgpu_info info;
     std::vector<double> xtraj(_output.xtraj.size()), utraj(_output.utraj.size());
-    mpcgpu_problem_desc d = _desc;
-    int rc = mpcgpu_solve_host(handle(1), 1, _params.xinit.data(), _loaded_x0.data(), _params.all_parameters.data(), xtraj.data(),
-                               utraj.data(), &info, nullptr);
-    (void)d;
+    mpcgpu_handle h = handle(1);
+    if (!persistent_multipliers) std::fill(_nlp_multipliers.begin(), _nlp_multipliers.end(), 0.0);
+    int rc = mpcgpu_set_state(h, 0, 1, _nlp_multipliers.data());
+    if (rc == 0)
+        rc = mpcgpu_solve_host(h, 1, _params.xinit.data(), _loaded_x0.data(), _params.all_parameters.data(), xtraj.data(), utraj.data(),
+                               &info, nullptr);
+    if (rc == 0) rc = mpcgpu_get_state(h, 0, 1, _nlp_multipliers.data());
     if (rc != 0) throw std::runtime_error(std::string("mpcgpu_solve_host: ") + mpcgpu_strerror(rc));
     storeResult(xtraj.data(), utraj.data(), info);
     _iteration_done = true;
@@ -124,9 +132,18 @@ int Solver::solveBatch(const std::vector<Solver *> &solvers, std::vector<int> &e
         std::copy(solvers[i]->_params.all_parameters.begin(), solvers[i]->_params.all_parameters.end(), par.begin() + i * np);
     }
     int best = -1;
-    int rc = mpcgpu_solve_host(lead->handle(P), P, xinit.data(), x0.data(), par.data(), xtraj.data(), utraj.data(), info.data(), &best);
+    // each Solver owns its multipliers (slot i of the launch <- solvers[i]'s, and back)
+    const size_t ns = lead->_nlp_multipliers.size();
+    std::vector<double> mult(P * ns, 0.0);
+    if (persistent_multipliers)
+        for (int i = 0; i < P; i++) std::copy(solvers[i]->_nlp_multipliers.begin(), solvers[i]->_nlp_multipliers.end(), mult.begin() + i * ns);
+    mpcgpu_handle h = lead->handle(P);
+    int rc = mpcgpu_set_state(h, 0, P, mult.data());
+    if (rc == 0) rc = mpcgpu_solve_host(h, P, xinit.data(), x0.data(), par.data(), xtraj.data(), utraj.data(), info.data(), &best);
+    if (rc == 0) rc = mpcgpu_get_state(h, 0, P, mult.data());
     if (rc != 0) throw std::runtime_error(std::string("mpcgpu_solve_host: ") + mpcgpu_strerror(rc));
     for (int i = 0; i < P; i++) {
+        std::copy(mult.begin() + i * ns, mult.begin() + (i + 1) * ns, solvers[i]->_nlp_multipliers.begin());
         solvers[i]->_info = Info();
         solvers[i]->storeResult(xtraj.data() + i * nxt, utraj.data() + i * nut, info[i]);
         solvers[i]->_iteration_done = true;

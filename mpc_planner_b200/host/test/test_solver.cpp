@@ -155,6 +155,26 @@ static void test_gpu(const char *in_path, const char *out_path) {
         CHECK(solvers[i]->getOutput(1, "x") == solvers[i]->_output.xtraj[1 * solvers[i]->nx + 0]);
         CHECK(solvers[i]->getOutput(0, "w") == solvers[i]->_output.utraj[1]);
     }
+    // second control step on `single`: parameters re-copied from solver 0 (operator= keeps single's solver memory),
+    // warm start = its own previous solution; the multipliers of the first solve enter the first exact Hessian.
+    CHECK(!single.nlpMultipliers().empty());
+    bool any_mult = false;
+    for (double v : single.nlpMultipliers()) any_mult = any_mult || v != 0.0;
+    CHECK(any_mult);
+    single = *solvers[0];
+    for (int k = 0; k < single.N; k++) {
+        single.setEgoPrediction(k, "a", single.getOutput(k, "a"));
+        single.setEgoPrediction(k, "w", single.getOutput(k, "w"));
+    }
+    for (int k = 0; k <= single.N; k++)
+        for (const char *name : {"x", "y", "psi", "v", "spline"}) single.setEgoPrediction(k, name, single.getOutput(k, name));
+    single.loadWarmstart();
+    int exit_second = single.solve();
+    std::fwrite(&exit_second, sizeof(int), 1, o);
+    std::fwrite(&single._info.pobj, sizeof(double), 1, o);
+    std::fwrite(single._output.xtraj.data(), sizeof(double), single._output.xtraj.size(), o);
+    single.reset();
+    for (double v : single.nlpMultipliers()) CHECK(v == 0.0);
     std::fclose(o);
     for (Solver *s : solvers) delete s;
 }

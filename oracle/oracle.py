@@ -60,9 +60,14 @@ def eval_stage(desc, z, p, lam=None, pi=None):
     return out
 
 
-def solve_batch(spec, xinit, x0, params, nthreads=0, iterates=False):
+def state_size(spec):
+    return int(lib().oracle_state_size(ctypes.byref(spec.desc())))
+
+
+def solve_batch(spec, xinit, x0, params, nthreads=0, iterates=False, state=None):
     """Solve P problems.  Arrays are [P, ...] in the reference's flat layouts.
-    Returns (xtraj[P,N+1,nx], utraj[P,N,nu], info(list of dict))  (+ iterates[P,n_sqp,N+1,nz])."""
+    Returns (xtraj[P,N+1,nx], utraj[P,N,nu], info(list of dict))  (+ iterates[P,n_sqp,N+1,nz]).
+    `state` [P, state_size] (in/out): persistent NLP multipliers of the P solvers (Solver::operator= semantics)."""
     from mpc_planner_b200.problem import SolveInfo
 
     desc = spec.desc()
@@ -76,7 +81,13 @@ def solve_batch(spec, xinit, x0, params, nthreads=0, iterates=False):
     xtraj = np.zeros((P, N + 1, nx))
     utraj = np.zeros((P, N, nu))
     info = (SolveInfo * P)()
-    if iterates:
+    if state is not None:
+        assert not iterates and state.flags.c_contiguous and state.dtype == np.float64 and state.shape == (P, state_size(spec))
+        for i in range(P):
+            rc = lib().oracle_solve_stateful(ctypes.byref(desc), _p(xinit[i]), _p(x0[i]), _p(params[i]), _p(xtraj[i]), _p(utraj[i]),
+                                             ctypes.byref(info[i]), _p(state[i]))
+            assert rc == 0
+    elif iterates:
         its = np.zeros((P, spec.n_sqp, N + 1, nz))
         for i in range(P):
             rc = lib().oracle_solve(ctypes.byref(desc), _p(xinit[i]), _p(x0[i]), _p(params[i]), _p(xtraj[i]), _p(utraj[i]),

@@ -16,7 +16,7 @@ extern "C" void emu_mirror_stats(long *calls, long *slow) { *calls = g_mirror_ca
 
 template <class CFG>
 static int solve_cfg(const mpcgpu_problem_desc &d, int P, const double *xinit, const double *x0, const double *params,
-                     double *xtraj, double *utraj, mpcgpu_info *info, double *iterates) {
+                     double *xtraj, double *utraj, mpcgpu_info *info, double *iterates, double *state) {
     typedef SL<CFG> S;
     const Layout L = make_layout(d);
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU;
@@ -28,7 +28,8 @@ static int solve_cfg(const mpcgpu_problem_desc &d, int P, const double *xinit, c
             for (int i = 0; i < d.npar; i++) pt[(size_t)i * 32 + k] = par[(size_t)k * d.npar + i];
         sqp_solve_cta<CFG>(L, sm.data(), xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt.data(),
                             xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p,
-                            iterates ? iterates + (size_t)p * d.n_sqp * (N + 1) * NZ : nullptr);
+                            iterates ? iterates + (size_t)p * d.n_sqp * (N + 1) * NZ : nullptr,
+                            state ? state + (size_t)p * ((N + 1) * NX + N * CFG::NH) : nullptr);
     }
     return 0;
 }
@@ -46,7 +47,17 @@ int emu_problem_supported(const mpcgpu_problem_desc *d) {
 int emu_solve(const mpcgpu_problem_desc *d, int P, const double *xinit, const double *x0, const double *params,
               double *xtraj, double *utraj, mpcgpu_info *info, double *iterates) {
 #define X(C) \
-    if (config_matches<C>(*d)) return solve_cfg<C>(*d, P, xinit, x0, params, xtraj, utraj, info, iterates);
+    if (config_matches<C>(*d)) return solve_cfg<C>(*d, P, xinit, x0, params, xtraj, utraj, info, iterates, nullptr);
+    MPCGPU_CONFIG_LIST(X)
+#undef X
+    return -2;
+}
+
+// as emu_solve with the persistent multipliers of P solve slots (P x mpcgpu_state_size doubles, in/out)
+int emu_solve_stateful(const mpcgpu_problem_desc *d, int P, const double *xinit, const double *x0, const double *params,
+                       double *xtraj, double *utraj, mpcgpu_info *info, double *state) {
+#define X(C) \
+    if (config_matches<C>(*d)) return solve_cfg<C>(*d, P, xinit, x0, params, xtraj, utraj, info, nullptr, state);
     MPCGPU_CONFIG_LIST(X)
 #undef X
     return -2;

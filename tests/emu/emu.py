@@ -61,7 +61,8 @@ def eval_stage(desc, z, p, lam=None, pi=None):
     return out
 
 
-def solve_batch(spec, xinit, x0, params, iterates=False, library=None):
+def solve_batch(spec, xinit, x0, params, iterates=False, library=None, state=None):
+    """`state` [P, state_size] (in/out, C-contiguous float64): persistent multipliers of the P solve slots."""
     from mpc_planner_b200.problem import SolveInfo
 
     desc = spec.desc()
@@ -73,7 +74,12 @@ def solve_batch(spec, xinit, x0, params, iterates=False, library=None):
     xtraj, utraj = np.zeros((P, N + 1, nx)), np.zeros((P, N, nu))
     info = (SolveInfo * P)()
     its = np.zeros((P, spec.n_sqp, N + 1, nz)) if iterates else None
-    rc = (ctypes.CDLL(library) if library else lib()).emu_solve(ctypes.byref(desc), P, _p(xinit), _p(x0), _p(params), _p(xtraj), _p(utraj), info, _p(its))
+    L = ctypes.CDLL(library) if library else lib()
+    if state is not None:
+        assert not iterates and state.flags.c_contiguous and state.dtype == np.float64 and state.shape[0] == P
+        rc = L.emu_solve_stateful(ctypes.byref(desc), P, _p(xinit), _p(x0), _p(params), _p(xtraj), _p(utraj), info, _p(state))
+    else:
+        rc = L.emu_solve(ctypes.byref(desc), P, _p(xinit), _p(x0), _p(params), _p(xtraj), _p(utraj), info, _p(its))
     if rc != 0:
         raise RuntimeError(f"emu_solve: {rc}")
     infos = [dict(pobj=i.pobj, res_eq=i.res_eq, res_stat_qp=i.res_stat_qp, res_comp_qp=i.res_comp_qp, exit_code=i.exit_code,

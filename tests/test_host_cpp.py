@@ -68,6 +68,25 @@ def test_cpp_solver_matches_python_binding(exe, tmp_path):
         assert pobj == info[i]["pobj"]  # same kernel, same inputs: bit-identical
         np.testing.assert_array_equal(cx, xt[i].ravel())
         np.testing.assert_array_equal(cu, ut[i].ravel())
+    # second control step of solver 0 with its own multipliers kept (Solver::operator= is parameters-only):
+    # equals the oracle run with persistent state
+    from oracle import oracle
+
+    (code2,) = struct.unpack_from("i", raw, off)
+    off += 4
+    (pobj2,) = struct.unpack_from("d", raw, off)
+    off += 8
+    cx2 = np.frombuffer(raw, dtype=np.float64, count=nxt, offset=off)
+    st = np.zeros((1, oracle.state_size(spec)))
+    o1 = oracle.solve_batch(spec, b["xinit"][:1], b["x0"][:1], b["params"][:1], state=st)
+    z = np.zeros((1, spec.N + 1, spec.nz))
+    z[:, : spec.N, : spec.nu] = o1[1]
+    z[:, :, spec.nu:] = o1[0]
+    o2 = oracle.solve_batch(spec, b["xinit"][:1], z.reshape(1, -1), b["params"][:1], state=st)
+    assert code2 == o2[2][0]["exit_code"]
+    if code2 == 1:
+        np.testing.assert_allclose(cx2, o2[0][0].ravel(), rtol=1e-6, atol=1e-6)
+        assert pobj2 == pytest.approx(o2[2][0]["pobj"], rel=1e-6)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,90 @@
+"""Persistent NLP multipliers per solver slot: `Solver::operator=` copies parameters only, so a
+reference LocalPlanner's acados memory -- the multipliers that enter the first exact Hessian -- survives from one
+control step to the next (acados_solver_interface.cpp:67-77).  Oracle and kernel (emulated here, real on the GPU)
+implement the same state [pi | multipliers of h] and must agree over consecutive control steps."""
+import numpy as np
+import pytest
+
+from mpc_planner_b200 import problem as pb, scenes
+from oracle import oracle
+from tests.emu import emu
+
+
+def two_steps(spec, solve, state):
+    """control step 1 on the scene, control step 2 warm-started at step 1's solution shifted by the applied input"""
+    b = scenes.make_scene_batch(spec, 2, 2, seed=21)
+    N, nu = spec.N, spec.nu
+    r1 = solve(b["xinit"], b["x0"], b["params"], state)
+    xt, ut = r1[0], r1[1]
+    z = np.zeros((xt.shape[0], N + 1, spec.nz))
+    z[:, :N, :nu] = ut
+    z[:, :, nu:] = xt
+    r2 = solve(b["xinit"], z.reshape(xt.shape[0], -1), b["params"], state)
+    return r1, r2
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_emulated_kernel_and_oracle_agree_over_two_stateful_steps(name):
+    spec = pb.CONFIGS[name]()
+    P = 4
+    so = np.zeros((P, oracle.state_size(spec)))
+    se = np.zeros_like(so)
+    o1, o2 = two_steps(spec, lambda a, b, c, st: oracle.solve_batch(spec, a, b, c, state=st), so)
+    e1, e2 = two_steps(spec, lambda a, b, c, st: emu.solve_batch(spec, a, b, c, state=st), se)
+    ok = np.array([i["exit_code"] == 1 for i in o2[2]]) & np.array([i["exit_code"] == 1 for i in o1[2]])
+    assert ok.any()
+    assert [i["exit_code"] for i in e2[2]] == [i["exit_code"] for i in o2[2]]
+    np.testing.assert_allclose(e2[0][ok], o2[0][ok], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(se[ok], so[ok], rtol=1e-5, atol=1e-6)
+    assert np.abs(so[ok]).max() > 1e-3  # active constraints / dynamics leave non-zero multipliers
+    # the state matters: a stateless second step takes a different first exact Hessian
+    z = np.zeros((P, spec.N + 1, spec.nz))
+    z[:, : spec.N, : spec.nu] = o1[1]
+    z[:, :, spec.nu:] = o1[0]
+    b = scenes.make_scene_batch(spec, 2, 2, seed=21)
+    fresh = oracle.solve_batch(spec, b["xinit"], z.reshape(P, -1), b["params"])
+    assert np.abs(fresh[0][ok] - o2[0][ok]).max() > 1e-13  # (both runs converge towards the same KKT point)
+
+
+def test_failed_solve_clears_the_slot():
+    spec = pb.config_tmpc()
+    b = scenes.make_scene_batch(spec, 1, 2, seed=3)
+    bad = b["params"].copy()
+    bad[0, :] = np.nan  # non-finite parameters: QP failure
+    st = np.ones((2, oracle.state_size(spec)))
+    _, _, info = oracle.solve_batch(spec, b["xinit"], b["x0"], bad, state=st)
+    assert info[0]["exit_code"] == 4 and not st[0].any()
+    se = np.ones_like(st)
+    _, _, info_e = emu.solve_batch(spec, b["xinit"], b["x0"], bad, state=se)
+    assert info_e[0]["exit_code"] == 4 and not se[0].any()
+    assert np.isfinite(se).all() and np.isfinite(st).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4"])
+def test_gpu_stateful_slots_match_oracle(name):
+    from mpc_planner_b200 import binding
+
+    spec = pb.CONFIGS[name]()
+    P = 4
+    solver = binding.BatchSolver(spec, P)
+    solver.set_stateful(True)
+    assert solver.state_size() == oracle.state_size(spec)
+    so = np.zeros((P, oracle.state_size(spec)))
+    o1, o2 = two_steps(spec, lambda a, b, c, st: oracle.solve_batch(spec, a, b, c, state=st), so)
+    g1, g2 = two_steps(spec, lambda a, b, c, st: solver.solve(a, b, c)[:3], None)
+    ok = np.array([i["exit_code"] == 1 for i in o2[2]]) & np.array([i["exit_code"] == 1 for i in o1[2]])
+    assert ok.any()
+    assert [i["exit_code"] for i in g2[2]] == [i["exit_code"] for i in o2[2]]
+    np.testing.assert_allclose(g2[0][ok], o2[0][ok], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(solver.get_state()[ok], so[ok], rtol=1e-5, atol=1e-6)
+    # reset == fresh solver; set_state restores a checkpoint
+    saved = solver.get_state()
+    solver.reset_state()
+    assert not solver.get_state().any()
+    b = scenes.make_scene_batch(spec, 2, 2, seed=21)
+    fresh_gpu = solver.solve(b["xinit"], b["x0"], b["params"])
+    np.testing.assert_allclose(fresh_gpu[0][ok], o1[0][ok], rtol=1e-6, atol=1e-6)
+    solver.set_state(saved)
+    np.testing.assert_array_equal(solver.get_state(), saved)
+    solver.close()
