@@ -67,8 +67,11 @@ def test_generated_cuda_library_builds_and_serves_only_its_stack():
 def test_generated_cuda_library_matches_oracle_on_gpu():
     spec = custom_spec()
     so = os.path.join(OUT, "libmpcgpu_custom_n16_o5.so")
-    if not os.path.exists(so):
-        so = generate.build_solver_library(spec, OUT)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    deps = [os.path.join(root, "include", "mpcgpu.h")] + [
+        os.path.join(root, "mpc_planner_b200", "csrc", f) for f in os.listdir(os.path.join(root, "mpc_planner_b200", "csrc"))]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        so = generate.build_solver_library(spec, OUT)  # nvcc is on the GPU box too
     b = scenes.make_scene_batch(spec, 4, 4, seed=8)
     solver = binding.BatchSolver(spec, 16, library=so)
     solver.set_group(4)
