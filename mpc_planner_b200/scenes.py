@@ -167,7 +167,10 @@ def make_scene_batch(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int, seed: 
                 direction = target_dir + mix * np.array([np.cos(hq), np.sin(hq)])
                 direction /= np.linalg.norm(direction)
                 traj = start[None, :] + (sp * t)[:, None] * direction[None, :]
-                if np.linalg.norm(traj[0] - pos0) > 1.8 and np.linalg.norm(traj[1] - pos0) > 1.5:
+                # not on top of the robot now, and not across its nominal motion during the first 1.6 s (an obstacle
+                # that close cannot be avoided with the bounded inputs: every guess would be infeasible)
+                early = np.linalg.norm(traj[:9] - base_pos[:9], axis=1).min()
+                if np.linalg.norm(traj[0] - pos0) > 1.8 and np.linalg.norm(traj[1] - pos0) > 1.5 and early > 1.5:
                     obs_pos[o] = traj
                     break
             else:
@@ -245,7 +248,8 @@ def make_scene_batch(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int, seed: 
             par = shared.copy()
             traj = np.zeros((N + 1, nz))
             guided = gi > 0 and n_obs > 0
-            for attempt in range(8):
+            best_clear, best_traj = -np.inf, None
+            for attempt in range(12):
                 bits = max(gi - 1, 0) if attempt == 0 else int(rng.integers(0, 2 ** max(len(relevant), 1)))
                 amp_jitter = 1.0 if (attempt == 0 and gi - 1 < 2 ** max(len(relevant), 1)) else rng.uniform(0.8, 1.5)
                 bump = 1.2 if attempt == 0 else rng.uniform(1.0, 2.0)
@@ -281,8 +285,11 @@ def make_scene_batch(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int, seed: 
                     (np.linalg.norm(traj[1:, [iz["x"], iz["y"]]] - obs_pos[o, 1:], axis=1).min() for o in range(n_obs)),
                     default=np.inf,
                 )
+                if clear > best_clear:
+                    best_clear, best_traj = clear, traj
                 if clear >= OBSTACLE_RADIUS + ROBOT_RADIUS - 0.12:  # warm start (nearly) collision-free
                     break
+            traj = best_traj  # the clearest attempt if none was collision-free
             if guided and n_lin:
                 for k in range(1, N):
                     for o in range(min(n_obs, n_lin)):
