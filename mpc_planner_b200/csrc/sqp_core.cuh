@@ -72,21 +72,7 @@ struct ParamP {
     MPC_HD double operator()(int i) const { return p[i]; }
 };
 
-MPC_HD double mpc_rsqrt(double x) {
-#if defined(__CUDA_ARCH__)
-    return rsqrt(x);
-#else
-    return 1.0 / sqrt(x);
-#endif
-}
-// reciprocal of a strictly positive, normal number
-MPC_HD double mpc_rcp(double x) {
-#if defined(__CUDA_ARCH__)
-    return __drcp_rn(x);
-#else
-    return 1.0 / x;
-#endif
-}
+
 
 // NaN-propagating running max
 MPC_HD void upd_max(double &acc, double v) {
