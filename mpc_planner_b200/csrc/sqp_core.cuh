@@ -459,6 +459,7 @@ MPC_DEV void riccati_solve(double *sm) {
             pv[i] = sm[N * S::STRIDE + S::GT + NU + i];  // terminal: pv_N = gt_N
             sm[N * S::STRIDE + S::PV + i] = pv[i];
         }
+#pragma unroll 2
         for (int k = N - 1; k >= 0; k--) {
             double *st = sm + k * S::STRIDE;
             const double *stn = st + S::STRIDE;
@@ -494,6 +495,7 @@ MPC_DEV void riccati_solve(double *sm) {
             dx[i] = W[S::W_DX0 + i];
             sm[S::DZN + NU + i] = dx[i];
         }
+#pragma unroll 2
         for (int k = 0; k < N; k++) {
             double *st = sm + k * S::STRIDE;
             double *stn = st + S::STRIDE;
