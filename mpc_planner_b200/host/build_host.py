@@ -34,3 +34,17 @@ def build_modules_test(name="cfg2", out_dir=None):
            os.path.join(HERE, "test", "test_modules.cpp"), "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-o", exe]
     subprocess.check_call(cmd)
     return exe
+
+
+def build_planner_test(name="cfg2", out_dir=None):
+    """Planner::solveMPC (host/src/planner.cpp) + the closed-loop driver."""
+    spec = pb.CONFIGS[name]()
+    out_dir = out_dir or os.path.join(HERE, "generated", name)
+    generate_solver(spec, out_dir)
+    exe = os.path.join(out_dir, "test_planner")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I" + out_dir, "-I" + os.path.join(HERE, "include"), "-I" + os.path.join(libbuild.ROOT, "include"),
+           os.path.join(HERE, "src", "cuda_solver_interface.cpp"), os.path.join(HERE, "src", "modules.cpp"), os.path.join(HERE, "src", "planner.cpp"),
+           os.path.join(HERE, "test", "test_planner.cpp"), "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-o", exe]
+    subprocess.check_call(cmd)
+    return exe

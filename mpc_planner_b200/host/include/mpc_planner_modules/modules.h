@@ -89,6 +89,7 @@ struct Config {
     int n_discs{1}, max_obstacles{8}, num_segments{5}, add_halfspaces{0}, decomp_max_constraints{12};
     bool use_tmpcpp{true}, enable_constraints{true};
     double selection_weight_consistency{1.0};
+    int n_paths{4};  // guidance_planner n_paths: guided planners (T-MPC++ adds the non-guided one)
 };
 Config &CONFIG();
 
@@ -106,6 +107,7 @@ class ControllerModule {
     virtual bool isDataReady(const RealTimeData &, std::string &) { return true; }
     virtual int optimize(State &, const RealTimeData &, ModuleData &) { return EXIT_CODE_NOT_OPTIMIZED_YET; }
     virtual void reset() {}
+    virtual bool isObjectiveReached(const State &, const RealTimeData &) { return true; }
     ModuleType type;
 
   protected:
@@ -129,6 +131,7 @@ class Contouring : public ControllerModule {
     void setParameters(const RealTimeData &data, const ModuleData &module_data, int k) override;
 
   private:
+    bool isObjectiveReached(const State &state, const RealTimeData &data) override;  // contouring.cpp:167-179
     void setSplineParameters(int k);
     std::shared_ptr<Spline2D> _spline;
     int _closest_segment{0}, _n_segments;

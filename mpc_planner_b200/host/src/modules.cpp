@@ -74,6 +74,11 @@ void Contouring::update(State &state, const RealTimeData &, ModuleData &module_d
     state.set("spline", closest_s);  // the solver's spline state starts at the closest point
     _closest_segment = std::min(_closest_segment, std::max(0, _spline->numSegments() - _n_segments));
 }
+bool Contouring::isObjectiveReached(const State &state, const RealTimeData &) {  // :167-179
+    if (!_spline) return false;
+    const Vec2 end = _spline->getPoint(_spline->length), pos = state.getPos();
+    return std::hypot(pos[0] - end[0], pos[1] - end[1]) < 1.0;
+}
 void Contouring::setParameters(const RealTimeData &, const ModuleData &, int k) {  // :50-92
     setSolverParameterContour(k, _solver->_params, CONFIG().weights.at("contour"));
     setSolverParameterLag(k, _solver->_params, CONFIG().weights.at("lag"));

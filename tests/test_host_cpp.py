@@ -11,6 +11,8 @@ from mpc_planner_b200 import problem as pb
 from mpc_planner_b200 import scenes
 from mpc_planner_b200.host import build_host
 
+CONFIG_N_PATHS = 4  # host Config::n_paths: index of the non-guided planner in GuidanceConstraints::planners_
+
 
 @pytest.fixture(scope="module")
 def exe():
@@ -239,3 +241,65 @@ def test_batched_tmpc_loop_matches_oracle(modules_exe, tmp_path, selected, consi
     np.testing.assert_array_equal(main_xtraj, planners[best]["xtraj"])  # guidance_constraints.cpp:382-384
     if selected >= 0:
         assert best == selected  # the consistency weight makes the previously selected guess win (:358-359)
+
+
+# ---------------------------------------------------------------------------------------------
+# Planner::solveMPC in closed loop (mpc_planner/src/planner.cpp:37-158)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def planner_exe():
+    return build_host.build_planner_test("cfg2")
+
+
+def test_planner_without_data_reports_failure_cpu(planner_exe):
+    r = subprocess.run([planner_exe, "cpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_planner_closed_loop_avoids_obstacles_and_follows_the_path(planner_exe, tmp_path):
+    """50 control steps of Planner::solveMPC on the CUDA backend (T-MPC++: 2 guided + 1 non-guided guesses per step in
+    one launch, warm start shifted forward, multipliers kept per local solver): the robot must stay clear of the three
+    crossing obstacles, make progress along the reference path and keep the MPC feasible."""
+    from mpc_planner_b200.scenes import OBSTACLE_RADIUS, ROBOT_RADIUS, _fit_path, _path_eval
+
+    n_steps, v_ref, dt = 50, 2.0, 0.2
+    coef, starts = _fit_path(1.0, 9, phase=0.3)
+    p0, d0 = _path_eval(coef, starts, np.array(0.5))
+    state = [p0[0], p0[1] + 0.05, float(np.arctan2(d0[1], d0[0])), 1.0, 0.5]
+    obstacles = []
+    for s_cross, t_cross, side, speed in ((6.0, 3.0, +1.0, 0.8), (12.0, 6.0, -1.0, 1.0), (18.0, 9.5, +1.0, 0.6)):
+        q, dq = _path_eval(coef, starts, np.array(s_cross))
+        nrm = np.array([-dq[1], dq[0]]) / np.hypot(*dq)
+        vel = -side * speed * nrm  # walks across the path, reaching it at t_cross
+        obstacles.append((q - vel * t_cross, vel))
+    scene, out = tmp_path / "scene.bin", tmp_path / "out.bin"
+    with open(scene, "wb") as f:
+        def wd(*vals):
+            f.write(struct.pack(f"{len(vals)}d", *[float(v) for v in vals]))
+        wd(*state)
+        wd(len(starts))
+        for i in range(len(starts)):
+            wd(*coef[i, 0], *coef[i, 1], starts[i])
+        wd(starts[-1] + 5.0)
+        wd(len(obstacles))
+        for pos, vel in obstacles:
+            wd(*pos, *vel)
+        wd(n_steps, v_ref)
+    r = subprocess.run([planner_exe, "gpu", str(scene), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.frombuffer(open(out, "rb").read(), dtype=np.float64)
+    assert int(raw[0]) == n_steps
+    rec = raw[1:].reshape(n_steps, 11)
+    success, exit_flag, best, x, y, psi, v, spline, a, w, clearance = rec.T
+    assert success.mean() >= 0.9, (success, exit_flag)
+    assert success[0] == 1.0
+    assert clearance.min() >= OBSTACLE_RADIUS + ROBOT_RADIUS - 0.05, clearance.min()
+    assert spline[-1] - spline[0] >= 0.6 * v_ref * dt * n_steps  # progress along the path
+    # contouring: the robot stays near the reference path except while passing an obstacle
+    pos_ref, _ = _path_eval(coef, starts, spline)
+    lateral = np.hypot(x - pos_ref[:, 0], y - pos_ref[:, 1])
+    assert lateral.max() < 3.0 and np.median(lateral) < 0.8
+    assert np.all(v >= -1e-6) and np.all(v <= 3.0 + 1e-6) and np.all(np.abs(w[success == 1]) <= 0.8 + 1e-6)
+    assert set(best[success == 1].astype(int)) <= {0, 1, CONFIG_N_PATHS}
