@@ -41,15 +41,16 @@ thread_local char g_last_cuda_error[256] = "";
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-// params[P][N][npar] (AcadosParameters::all_parameters, stage-major) -> pt[P][npar][32]
+// params[P][N][npar] (AcadosParameters::all_parameters, stage-major) -> pt[P][npar][pt_stride(N)]
 __global__ void transpose_params_kernel(const double *__restrict__ params, double *__restrict__ pt, int P, int N, int npar) {
     const long long total = (long long)P * N * npar;
+    const int PT = pt_stride(N);
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(idx % npar);
         const long long pk = idx / npar;
         const int k = (int)(pk % N);
         const long long p = pk / N;
-        pt[(p * npar + i) * 32 + k] = params[idx];
+        pt[(p * npar + i) * PT + k] = params[idx];
     }
 }
 
@@ -66,10 +67,11 @@ __global__ void pack_tmpc_kernel(const double *__restrict__ scene_params, const 
     const int p = blockIdx.x, s = p / G, g = p - s * G;
     if (s >= S) return;
     const double *sp = scene_params + (size_t)s * N * npar;
-    double *ptp = pt + (size_t)p * npar * 32;
+    const int PT = pt_stride(N);
+    double *ptp = pt + (size_t)p * npar * PT;
     for (int idx = threadIdx.x; idx < N * npar; idx += blockDim.x) {
         const int k = idx / npar, i = idx - k * npar;
-        ptp[i * 32 + k] = sp[idx];
+        ptp[i * PT + k] = sp[idx];
     }
     if (threadIdx.x < nx) xinit_out[(size_t)p * nx + threadIdx.x] = xinit_scene[(size_t)s * nx + threadIdx.x];
     __syncthreads();
@@ -102,9 +104,9 @@ __global__ void pack_tmpc_kernel(const double *__restrict__ scene_params, const 
                 a2 = dy / dist;
                 b = a1 * ox + a2 * oy - R;
             }
-            ptp[(lin0 + 3 * j) * 32 + k] = a1;
-            ptp[(lin0 + 3 * j + 1) * 32 + k] = a2;
-            ptp[(lin0 + 3 * j + 2) * 32 + k] = b;
+            ptp[(lin0 + 3 * j) * PT + k] = a1;
+            ptp[(lin0 + 3 * j + 1) * PT + k] = a2;
+            ptp[(lin0 + 3 * j + 2) * PT + k] = b;
         }
     }
 }
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(MPC_NT, sqp_min_ctas<CFG>()) sqp_kernel(Layout
         s_serial_tid = (int)((atomicAdd(&sm_slots[smid & 255], 1u) % (MPC_NT / 32)) * 32);
     }
     __syncthreads();
-    sqp_solve_cta<CFG>(L, sm, xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt + (size_t)p * L.npar * 32,
+    sqp_solve_cta<CFG>(L, sm, xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt + (size_t)p * L.npar * pt_stride(N),
                         xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p, nullptr,
                         state ? state + (size_t)p * ((N + 1) * NX + N * CFG::NH) : nullptr, s_serial_tid);
 }
@@ -328,7 +330,7 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     ok = ok && cudaMalloc(&h->d_xinit, B * h->n_xinit * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_x0, B * h->n_x0 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_params, B * h->n_params * sizeof(double)) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_pt, B * (size_t)desc->npar * 32 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_pt, B * (size_t)desc->npar * pt_stride(desc->N) * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_xtraj, B * h->n_xtraj * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_utraj, B * h->n_utraj * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_info, B * sizeof(mpcgpu_info)) == cudaSuccess;
@@ -336,7 +338,7 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     ok = ok && cudaMalloc(&h->d_sm_slots, 256 * sizeof(unsigned int)) == cudaSuccess;
     if (ok) ok = cudaMemset(h->d_sm_slots, 0, 256 * sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
-    if (ok) ok = cudaMemset(h->d_pt, 0, B * (size_t)desc->npar * 32 * sizeof(double)) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->d_pt, 0, B * (size_t)desc->npar * pt_stride(desc->N) * sizeof(double)) == cudaSuccess;
     if (!ok) {
         snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         mpcgpu_destroy(h);
@@ -379,7 +381,7 @@ int mpcgpu_destroy(mpcgpu_handle h) {
 static int enqueue_solve(mpcgpu_handle h, int slot, int count, const double *d_xinit, const double *d_x0, const double *d_params,
                          double *d_xtraj, double *d_utraj, mpcgpu_info *d_info, int *d_best, cudaStream_t s, bool timed) {
     const int N = h->desc.N, npar = h->desc.npar;
-    double *pt = h->d_pt + (size_t)slot * npar * 32;
+    double *pt = h->d_pt + (size_t)slot * npar * pt_stride(N);
     const long long total = (long long)count * N * npar;
     int tb = (int)((total + 255) / 256);
     if (tb > 148 * 16) tb = 148 * 16;
@@ -510,11 +512,11 @@ int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, c
         cudaStream_t sc = (c & 1) ? h->stream2 : h->stream;
         CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
         pack_tmpc_kernel<<<(unsigned)np, 128, 0, sc>>>(h->d_params + s0 * h->n_params, h->d_xinit_scene + s0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_guided,
-                                                       h->d_pt + p0 * (size_t)d.npar * 32, h->d_xinit + p0 * h->n_xinit, (int)ns, G, d.N, d.npar, d.nx, d.nu,
+                                                       h->d_pt + p0 * (size_t)d.npar * pt_stride(d.N), h->d_xinit + p0 * h->n_xinit, (int)ns, G, d.N, d.npar, d.nx, d.nu,
                                                        d.con_param[m_lin], d.con_count[m_lin], d.con_param[m_obs], obs_stride, n_obs, robot_radius);
         const bool timed = h->timing != 0 && n_chunks == 1;
         if (timed) cudaEventRecord(h->ev0, sc);
-        h->kt->launch_sqp(h->layout, (int)np, h->d_xinit + p0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_pt + p0 * (size_t)d.npar * 32,
+        h->kt->launch_sqp(h->layout, (int)np, h->d_xinit + p0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_pt + p0 * (size_t)d.npar * pt_stride(d.N),
                           h->d_xtraj + p0 * h->n_xtraj, h->d_utraj + p0 * h->n_utraj, h->d_info + p0, h->d_sm_slots,
                           h->d_state ? h->d_state + p0 * h->n_state : nullptr, h->kt->smem_bytes, sc);
         if (timed) cudaEventRecord(h->ev1, sc);

@@ -54,15 +54,16 @@ constexpr int MPC_RED_SLOTS = MPC_NT;
 #endif
 enum { TK_LIN = 0, TK_ASM, TK_INIT, TK_PA, TK_PB, TK_ACC0, TK_RED, TK_FACTOR, TK_SOLVE, TK_PD, TK_ACC1, TK_PF, TK_STEP, TK_FINAL };
 
-// parameter accessor over the per-solve transposed parameter block pt[npar][32] (column = stage)
+// parameter accessor over the per-solve transposed parameter block pt[npar][PT] (column = stage, PT = pt_stride(N))
+template <int PT>
 struct ParamT {
     const double *base;
     int k;
     MPC_HD double operator()(int i) const {
 #if defined(__CUDA_ARCH__)
-        return __ldg(base + i * 32 + k);
+        return __ldg(base + i * PT + k);
 #else
-        return base[i * 32 + k];
+        return base[i * PT + k];
 #endif
     }
 };
@@ -936,7 +937,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
 
 // ---------------------------------------------------------------------------------------------
 // The whole solve.  sm: SL<CFG>::TOTAL doubles of CTA-private shared memory.
-//   xinit[NX], x0[(N+1)*NZ] (reference layout), pt = parameters transposed to [npar][32]
+//   xinit[NX], x0[(N+1)*NZ] (reference layout), pt = parameters transposed to [npar][pt_stride(N)]
 //   xtraj[(N+1)*NX], utraj[N*NU], info; iterates (may be null): [n_sqp][N+1][NZ]
 // ---------------------------------------------------------------------------------------------
 template <class CFG>
@@ -945,7 +946,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
                            int serial_tid = 0) {
     typedef SL<CFG> S;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NT = MPC_NT;
-    static_assert(N + 1 <= 32, "parameters are staged in 32 columns");
+    static_assert(N + 1 <= 32, "one stage per lane");
     double *W = sm + S::W_BASE;
     double *mpc_prof = W + S::W_PROF;
     (void)mpc_prof;
@@ -992,7 +993,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         MPC_PHASE
         for (int it = tid; it < 6 * N; it += NT) {
             const int part = it / N, k = it - part * N;  // same part in neighbouring threads
-            ParamT pa{pt, k};
+            ParamT<pt_stride(N)> pa{pt, k};
             linearize_part<CFG>(pa, L, sm + k * S::STRIDE, sm + (k + 1) * S::STRIDE, k, part);
         }
         if (tid >= NT - NX) {
@@ -1048,7 +1049,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     {
         double c = 0.0, defect = 0.0;
         if (tid < N) {
-            ParamT pa{pt, tid};
+            ParamT<pt_stride(N)> pa{pt, tid};
             const double *st = sm + tid * S::STRIDE, *stn = sm + (tid + 1) * S::STRIDE;
             double z[NZ], xn[NX];
 #pragma unroll

@@ -20,12 +20,12 @@ static int solve_cfg(const mpcgpu_problem_desc &d, int P, const double *xinit, c
     typedef SL<CFG> S;
     const Layout L = make_layout(d);
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU;
-    std::vector<double> sm(S::TOTAL), pt((size_t)d.npar * 32);
+    std::vector<double> sm(S::TOTAL), pt((size_t)d.npar * pt_stride(N));
     for (int p = 0; p < P; p++) {
         const double *par = params + (size_t)p * d.npar * N;
         std::fill(pt.begin(), pt.end(), 0.0);
         for (int k = 0; k < N; k++)
-            for (int i = 0; i < d.npar; i++) pt[(size_t)i * 32 + k] = par[(size_t)k * d.npar + i];
+            for (int i = 0; i < d.npar; i++) pt[(size_t)i * pt_stride(N) + k] = par[(size_t)k * d.npar + i];
         sqp_solve_cta<CFG>(L, sm.data(), xinit + (size_t)p * NX, x0 + (size_t)p * NZ * (N + 1), pt.data(),
                             xtraj + (size_t)p * NX * (N + 1), utraj + (size_t)p * NU * N, info + p,
                             iterates ? iterates + (size_t)p * d.n_sqp * (N + 1) * NZ : nullptr,
