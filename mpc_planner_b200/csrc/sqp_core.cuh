@@ -927,7 +927,10 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
             rows_phase<CFG, RP_STEP>(L, sm, c);
         }
         MPC_TICK(TK_PF)
-        alpha = 0.995 / fmax(1.0, red_get<CFG>(W, 0, 0));  // fraction to the boundary; never a full step
+        {   // fraction-to-the-boundary rule: alpha = min(1, 0.995 alpha_max), alpha_max = 1 / max_rows(-d/val)
+            const double inv_amax = red_get<CFG>(W, 0, 0);
+            alpha = (inv_amax > 0.995) ? 0.995 / inv_amax : 1.0;
+        }
         if (!(sigma_mu == sigma_mu) || !(alpha == alpha)) { status = 4; break; }
         if (alpha < ALPHA_MIN) { status = 3; break; }
     }

@@ -131,8 +131,8 @@ class ProblemSpec:
     qp_mu0: float = 1e1
     qp_thr0: float = 1e-1
     qp_warm_start: int = 2  # generate_acados_solver.py:173
-    qp_ws_thr: float = 1e-2
-    qp_ws_mu: float = 1e-3
+    qp_ws_thr: float = 1e-4
+    qp_ws_mu: float = 1e-5
     qp_relax: float = 1e-7
     res_eq_fail: float = 1e-2  # acados_solver_interface.cpp:176
 
