@@ -138,7 +138,8 @@ struct SL {
     static constexpr int W_LB = W_DX0 + NX;     // NZ lower bounds (copy of Layout, for dynamic indexing)
     static constexpr int W_UB = W_LB + NZ;      // NZ upper bounds
     static constexpr int W_STID = W_UB + NZ;    // id of the thread that runs the serial Riccati sweeps
-    static constexpr int W_PROF = W_STID + 1;   // 32 doubles (profiling builds)
+    static constexpr int W_MBUF = W_STID + 1;   // lane-cooperative factorisation: double-buffered staging tile (packed lower NZ x NZ)
+    static constexpr int W_PROF = W_MBUF + 2 * NHP;  // 32 doubles (profiling builds)
 #if defined(MPC_PROFILE)
     static constexpr int W_SIZE = W_PROF + 32;
 #else
@@ -195,12 +196,23 @@ MPC_HD double red_combine(int kind, double a, double b) {
     return (b != b || b > a) ? b : a;
 }
 
+// kind 0 is only used on values that are >= +0 or NaN (maxima of fabs / ratio tests started at 0): for those the IEEE
+// bit pattern, read as an unsigned integer, is monotone and every NaN sorts above +inf, so the NaN-propagating max is an
+// integer max -- two REDUX.MAX per warp instead of five double shuffles + compare/select chains (and far less code:
+// the reductions were 11 KB of the kernel's instruction footprint).
 template <class CFG>
 MPC_DEV void red_put(double *W, int tid, int q, int kind, double v) {
     typedef SL<CFG> S;
 #if defined(__CUDA_ARCH__)
+    if (kind == 0) {
+        const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu, lo = (unsigned)__double2loint(v);  // (-0 -> +0)
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, (hi == mh) ? lo : 0u);
+        v = __hiloint2double((int)mh, (int)ml);
+    } else {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = red_combine(kind, v, __shfl_xor_sync(0xffffffffu, v, off));
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    }
     if ((tid & 31) == 0) W[S::W_RED + q * MPC_RED_SLOTS + (tid >> 5)] = v;
 #else
     W[S::W_RED + q * MPC_RED_SLOTS + tid] = v;
@@ -210,6 +222,17 @@ MPC_DEV void red_put(double *W, int tid, int q, int kind, double v) {
 template <class CFG>
 MPC_DEV double red_get(const double *W, int q, int kind) {
     typedef SL<CFG> S;
+#if defined(__CUDA_ARCH__)
+    if (kind == 0) {
+        unsigned long long m = (unsigned long long)__double_as_longlong(W[S::W_RED + q * MPC_RED_SLOTS]);
+#pragma unroll
+        for (int i = 1; i < MPC_RED_SLOTS; i++) {
+            const unsigned long long o = (unsigned long long)__double_as_longlong(W[S::W_RED + q * MPC_RED_SLOTS + i]);
+            m = o > m ? o : m;
+        }
+        return __longlong_as_double((long long)m);
+    }
+#endif
     double v = W[S::W_RED + q * MPC_RED_SLOTS];
 #pragma unroll
     for (int i = 1; i < MPC_RED_SLOTS; i++) v = red_combine(kind, v, W[S::W_RED + q * MPC_RED_SLOTS + i]);
@@ -443,8 +466,270 @@ MPC_DEV void riccati_factor(double *sm) {
     MPC_PHASE_END
 }
 
-// Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PIN.
+// ---------------------------------------------------------------------------------------------
+// Lane-cooperative backward factorisation (one warp, lane = column of the stage KKT block).
+//
+// A lone thread issues one FP64 instruction per two cycles with 1 of 32 lanes useful: the serial
+// factorisation above is bound by the FP64 pipe's ISSUE rate, not by its dependency chain.  Here lane j < NZ owns
+// column j of  M = H + G + [B A]' P+ [B A]  and lane NZ carries the vector recursion of the affine right-hand side
+// (m = gt + [B A]'(pv+ + P+ c)), which has exactly the algebra of one more column -- so the backward
+// sweep of the predictor solve rides along for free.  Per stage:
+//   step A (no communication): column of W = P+ [B A | c] (P+ replicated in every lane's registers), column of M;
+//          the columns go to a double-buffered staging tile (packed lower NZ x NZ) in shared memory;     __syncwarp
+//   step B (replicated): every lane reads the lower triangle, forms L_uu, L_xu and the Schur complement P
+//          (so P is again replicated: ONE exchange per stage), plus the Schur update of its own column
+//          (P column -> shared memory; for the vector lane: y and pv).
+// The host emulation runs the lanes of each step one after the other.
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+#define MPC_LANES_BEGIN {
+#define MPC_LANES_END \
+    }                 \
+    __syncwarp();
+#define MPC_LANES_END_NOSYNC }
+#define MPC_LV(x) x
+#define MPC_LANE_DECL(T, name, n) T name[n]
+#else
+#define MPC_LANES_BEGIN for (int lane = 0; lane < NL; ++lane) {
+#define MPC_LANES_END }
+#define MPC_LANES_END_NOSYNC }
+#define MPC_LV(x) x[lane]
+#define MPC_LANE_DECL(T, name, n) T name[32][n]
+#endif
+
+// Hides how a per-lane table entry was derived from the lane id: the compiler then keeps the entry in a register and
+// predicates on it instead of re-deriving it through (divergent) branches in the stage loop.
+MPC_DEV void mpc_opaque(int &v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(v));
+#else
+    (void)v;
+#endif
+}
+
+MPC_DEV void mpc_opaque(double *&v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(v));
+#else
+    (void)v;
+#endif
+}
+
 template <class CFG>
+MPC_DEV void riccati_factor_lanes(double *sm) {
+    typedef SL<CFG> S;
+    typedef RicIdx<CFG> R;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
+    constexpr int NL = NZ + 1;  // active lanes: NZ matrix columns + the vector lane
+    static_assert(NU == 2 && NL <= 32, "input block is factorised in closed form for nu = 2");
+    double *W = sm + S::W_BASE;
+    const int serial_tid = (int)W[S::W_STID];
+    MPC_PHASE
+#if defined(__CUDACC__)
+    if ((tid & ~31) == serial_tid) {
+        const int lane_raw = tid & 31;
+        const int lane = lane_raw < NL ? lane_raw : NL - 1;  // surplus lanes shadow the vector lane (no stores)
+        const bool live = lane_raw < NL;
+#else
+    if (tid == serial_tid) {
+        const bool live = true;
+#endif
+        MPC_LANE_DECL(double, Pn, S::NPP);   // P+ (replicated)
+        MPC_LANE_DECL(double, add, NX);      // vector lane: pv+; matrix lanes: 0
+        MPC_LANE_DECL(double, Mc, NZ);       // own column of M (vector lane: m)
+        MPC_LANE_DECL(double, Wc, NX);       // own column of W
+        MPC_LANE_DECL(int, hoff, NZ);        // offsets of the own column of H (vector lane: GT)
+        MPC_LANE_DECL(int, cinfo, 4);        // column of [B A | c]: offset, stride, present, identity row
+        MPC_LANE_DECL(int, goff, 4);         // barrier block entries of the own column: rows x, y, psi; slack row
+        MPC_LANE_DECL(int, gflag, 2);        // own column in the (x, y, psi) block; slack row entry present
+        MPC_LANE_DECL(int, sto, 4);          // where the own (o0, o1) pair and the own Schur column go; row mask of the latter; flags
+        MPC_LANES_BEGIN
+        const bool vec = (lane == NZ);
+#pragma unroll
+        for (int e = 0; e < S::NPP; e++) MPC_LV(Pn)[e] = sm[N * S::STRIDE + S::P + e];
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+            const double g = sm[N * S::STRIDE + S::GT + NU + i];  // terminal: pv_N = gt_N
+            MPC_LV(add)[i] = vec ? g : 0.0;
+            if (vec && live) sm[N * S::STRIDE + S::PV + i] = g;
+        }
+#pragma unroll
+        for (int i = 0; i < NZ; i++) MPC_LV(hoff)[i] = vec ? (S::GT + i) : (S::H + trisym(i, lane < NZ ? lane : 0));
+        {
+            int ofs = 0, str = 0, has = 0, idr = -1;
+            if (vec) {
+                ofs = S::C; str = 1; has = 1;
+            } else if (lane < NU) {
+                ofs = S::BB + lane; str = NU; has = 1;
+            } else {
+                idr = lane - NU;
+                const int e = R::eidx(idr);
+                if (e >= 0) { ofs = S::BE + e; str = NE; has = 1; }
+            }
+            MPC_LV(cinfo)[0] = ofs; MPC_LV(cinfo)[1] = str; MPC_LV(cinfo)[2] = has; MPC_LV(cinfo)[3] = idr;
+            const int aj = (lane == CFG::IX) ? 0 : (lane == CFG::IY) ? 1 : (lane == CFG::IPSI) ? 2 : -1;
+            const int ajc = aj >= 0 ? aj : 0;
+#pragma unroll
+            for (int a = 0; a < 3; a++) MPC_LV(goff)[a] = S::GB + trisym(a, ajc);
+            MPC_LV(gflag)[0] = (aj >= 0);
+            // slack row of the own column: GS[aj] under an (x, y, psi) column, GS[3] under the slack column
+            MPC_LV(goff)[3] = S::GS + ((CFG::ANY_SLACK_ROWS && lane == CFG::ISLACK) ? 3 : ajc);
+            MPC_LV(gflag)[1] = CFG::ANY_SLACK_ROWS && (aj >= 0 || lane == CFG::ISLACK);
+            MPC_LV(sto)[0] = vec ? S::YV : S::LXU + (lane >= NU ? lane - NU : 0) * NU;
+            MPC_LV(sto)[1] = vec ? S::PV : S::P + (lane >= NU ? lane - NU : 0);
+            {   // rows of the own Schur column that are stored: vector lane: all of pv; x lane: the lower triangle of P
+                int mask = 0;
+#pragma unroll
+                for (int i = 0; i < NX; i++) mask |= ((int)live & ((int)vec | ((int)(lane >= NU) & (int)(i >= lane - NU)))) << i;
+                MPC_LV(sto)[2] = mask;
+                // flags: 1 vector lane, 2 store (o0, o1), 4 store L_uu, 8 live vector lane, 16.. rows of the staging tile
+                int fl = (int)vec | (((int)live & (int)(lane >= NU)) << 1) | (((int)live & (int)(lane == 0)) << 2) | (((int)live & (int)vec) << 3);
+#pragma unroll
+                for (int i = 0; i < NZ; i++) fl |= ((int)live & (int)(lane < NZ) & (int)(i >= lane)) << (4 + i);
+                MPC_LV(sto)[3] = fl;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                mpc_opaque(MPC_LV(sto)[i]);
+                mpc_opaque(MPC_LV(cinfo)[i]);
+                mpc_opaque(MPC_LV(goff)[i]);
+            }
+            mpc_opaque(MPC_LV(gflag)[0]);
+            mpc_opaque(MPC_LV(gflag)[1]);
+#pragma unroll
+            for (int i = 0; i < NZ; i++) mpc_opaque(MPC_LV(hoff)[i]);
+        }
+        MPC_LANES_END_NOSYNC
+        for (int k = N - 1; k >= 0; k--) {
+            double *st = sm + k * S::STRIDE;
+            double *stn = st + S::STRIDE;
+            double *buf = W + S::W_MBUF + (k & 1) * S::NHP;
+            // ---- step A: own column of W and of M ----
+            MPC_LANES_BEGIN
+            const int fl = MPC_LV(sto)[3];
+            double col[NX];
+#pragma unroll
+            for (int l = 0; l < NX; l++) {
+                double v = MPC_LV(cinfo)[2] ? st[MPC_LV(cinfo)[0] + MPC_LV(cinfo)[1] * l] : 0.0;
+                if (l == MPC_LV(cinfo)[3]) v += 1.0;
+                col[l] = v;
+            }
+            // short dependency chains throughout: the FP64 pipe's result latency, not its issue rate, bounds this loop
+#pragma unroll
+            for (int l = 0; l < NX; l++) {
+                double t0 = MPC_LV(Pn)[trisym(l, 0)] * col[0];
+                double t1 = MPC_LV(Pn)[trisym(l, NX - 1)] * col[NX - 1];
+#pragma unroll
+                for (int m = 1; m < NX - 1; m++) {
+                    if (m & 1) t0 += MPC_LV(Pn)[trisym(l, m)] * col[m];
+                    else t1 += MPC_LV(Pn)[trisym(l, m)] * col[m];
+                }
+                const double acc = t0 + t1;
+                if (fl & 8) stn[S::PC + l] = acc;  // P+ c (vector lane)
+                MPC_LV(Wc)[l] = acc + MPC_LV(add)[l];
+            }
+#pragma unroll
+            for (int i = 0; i < NZ; i++) {
+                double acc = st[MPC_LV(hoff)[i]];  // H / gradient part (+ barrier terms below)
+                double dot = 0.0;                  // [B A]' W part
+                if (i < NU) {
+                    bool firstt = true;
+#pragma unroll
+                    for (int l = 0; l < NX; l++)
+                        if (R::bnz(l, i < NU ? i : 0)) {
+                            const double b = st[S::BB + l * NU + (i < NU ? i : 0)];
+                            dot = firstt ? b * MPC_LV(Wc)[l] : dot + b * MPC_LV(Wc)[l];
+                            firstt = false;
+                        }
+                } else {
+                    dot = MPC_LV(Wc)[i >= NU ? i - NU : 0];
+                    const int e = R::eidx(i >= NU ? i - NU : 0);
+                    if (e >= 0) {
+#pragma unroll
+                        for (int l = 0; l < NX; l++)
+                            if (R::enz(l, e >= 0 ? e : 0)) dot += st[S::BE + l * NE + (e >= 0 ? e : 0)] * MPC_LV(Wc)[l];
+                    }
+                }
+                {   // barrier Hessian terms of entry (i, lane): unconditional loads + selects (a lane-dependent branch
+                    // costs a divergence/reconvergence round trip per use)
+                    const double gd = st[S::GD + i];
+                    acc += (i == lane) ? gd : 0.0;
+                    const int ai = (i == CFG::IX) ? 0 : (i == CFG::IY) ? 1 : (i == CFG::IPSI) ? 2 : -1;
+                    if (ai >= 0) {
+                        const double gb = st[MPC_LV(goff)[ai >= 0 ? ai : 0]];
+                        acc += MPC_LV(gflag)[0] ? gb : 0.0;
+                    }
+                    if (CFG::ANY_SLACK_ROWS) {
+                        if (ai >= 0) {  // (xyz row, slack column)
+                            const double gs = st[S::GS + (ai >= 0 ? ai : 0)];
+                            acc += (lane == CFG::ISLACK) ? gs : 0.0;
+                        }
+                        if (i == CFG::ISLACK) {  // (slack row, xyz or slack column)
+                            const double gs = st[MPC_LV(goff)[3]];
+                            acc += MPC_LV(gflag)[1] ? gs : 0.0;
+                        }
+                    }
+                    acc += dot;
+                    if ((fl >> (4 + i)) & 1) buf[tri(i, 0) + lane] = acc;  // lower triangle, packed
+                }
+                MPC_LV(Mc)[i] = acc;
+            }
+            MPC_LANES_END
+            // ---- step B: replicated Schur complement + own column ----
+            MPC_LANES_BEGIN
+            const int fl = MPC_LV(sto)[3];
+            const bool vec = fl & 1;
+            // L_uu = chol(M_uu) with the two reciprocal square roots independent of each other:
+            //   1/l11 = rsqrt(m11 - m10^2/m00) = sqrt(m00) rsqrt(m00 m11 - m10^2)
+            const double m00 = buf[tri(0, 0)], m10 = buf[tri(1, 0)], m11 = buf[tri(1, 1)];
+            const double il00 = mpc_rsqrt(m00);
+            const double rdet = mpc_rsqrt(m11 * m00 - m10 * m10);
+            const double l10 = m10 * il00;
+            const double il11 = rdet * (m00 * il00);
+            const double cx = l10 * il00 * il11;
+            double Lx[NX][NU];
+#pragma unroll
+            for (int i = 0; i < NX; i++) {  // L_xu = M_xu L_uu^-T
+                const double b0 = buf[tri(NU + i, 0)], b1 = buf[tri(NU + i, 1)];
+                Lx[i][0] = b0 * il00;
+                Lx[i][1] = b1 * il11 - b0 * cx;
+            }
+#pragma unroll
+            for (int i = 0; i < NX; i++)
+#pragma unroll
+                for (int j = 0; j <= i; j++)
+                    MPC_LV(Pn)[tri(i, j)] = (buf[tri(NU + i, NU + j)] - Lx[i][1] * Lx[j][1]) - Lx[i][0] * Lx[j][0];
+            // own column: (o0, o1) = L_uu^-1 [M_0j; M_1j];  x rows minus L_xu (o0, o1)'
+            const double o0 = MPC_LV(Mc)[0] * il00;
+            const double o1 = MPC_LV(Mc)[1] * il11 - MPC_LV(Mc)[0] * cx;
+            {   // stores under simple predicates (no lane-dependent branches)
+                if (fl & 2) {  // vector lane: y;  x lanes: row of L_xu
+                    st[MPC_LV(sto)[0]] = o0;
+                    st[MPC_LV(sto)[0] + 1] = o1;
+                }
+                if (fl & 4) {
+                    st[S::LUU] = il00;
+                    st[S::LUU + 1] = l10;
+                    st[S::LUU + 2] = il11;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+                const double v = (MPC_LV(Mc)[NU + i] - Lx[i][1] * o1) - Lx[i][0] * o0;
+                MPC_LV(add)[i] = vec ? v : 0.0;
+                // vector lane: pv_i;  x lane: P(i, lane - NU) of the lower triangle
+                double *dst = st + MPC_LV(sto)[1] + (vec ? i : tri(i, 0));
+                mpc_opaque(dst);  // address formed unconditionally: the store below is one predicated instruction
+                if ((MPC_LV(sto)[2] >> i) & 1) *dst = v;
+            }
+            MPC_LANES_END_NOSYNC
+        }
+    }
+    MPC_PHASE_END
+}
+
+// Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PIN.
+template <class CFG, bool BACKWARD = true>
 MPC_DEV void riccati_solve(double *sm) {
     typedef SL<CFG> S;
     typedef RicIdx<CFG> R;
@@ -454,6 +739,8 @@ MPC_DEV void riccati_solve(double *sm) {
     MPC_PHASE
     if (tid == serial_tid) {
         // backward: m = gt + BA'(pv+ + P+ c);  y = Luu^-1 m_u;  pv = m_x - Lxu y
+        // (BACKWARD = false: riccati_factor_lanes already ran this sweep for the current gradient)
+        if (BACKWARD) {
         double pv[NX];
 #pragma unroll
         for (int i = 0; i < NX; i++) {
@@ -488,6 +775,7 @@ MPC_DEV void riccati_solve(double *sm) {
                 pv[i] = mx - st[S::LXU + i * NU] * y0 - st[S::LXU + i * NU + 1] * y1;
                 st[S::PV + i] = pv[i];
             }
+        }
         }
         // forward: du = -Luu^-T (y + Lxu' dx);  dx+ = c + B du + A dx
         double dx[NX];
@@ -625,6 +913,7 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
             if (NH > 0 && k >= 1 && k < N) {
                 if (heavy) {
                     double gb0 = 0.0, gb1 = 0.0, gb2 = 0.0, gs = 0.0;
+#pragma unroll 4
                     for (int j = 0; j < NH; j++) {
                         const double l = st[S::LAM + 2 * NZ + j], ti = st[S::TINV + 2 * NZ + j];
                         const double ja = st[S::JR + 3 * j + a];
@@ -886,9 +1175,15 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
         if (rs < L.qp_tol && re < L.qp_tol && ri < L.qp_tol && rc < L.qp_tol) { status = 0; break; }
         if (iter >= L.qp_iter_max) { status = 2; break; }
 
+#if defined(MPC_RICCATI_SERIAL)
         riccati_factor<CFG>(sm);
         MPC_TICK(TK_FACTOR)
-        riccati_solve<CFG>(sm);
+        riccati_solve<CFG, true>(sm);
+#else
+        riccati_factor_lanes<CFG>(sm);  // + backward sweep of the predictor right-hand side
+        MPC_TICK(TK_FACTOR)
+        riccati_solve<CFG, false>(sm);
+#endif
         MPC_TICK(TK_SOLVE)
         sigma_mu = 0.0;
         if (nc > 0) {
@@ -914,7 +1209,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
             // ---- PE: corrector gradient and solve ----
             stage_accumulate<CFG, 1>(L, sm, sigma_mu);
             MPC_TICK(TK_ACC1)
-            riccati_solve<CFG>(sm);
+            riccati_solve<CFG, true>(sm);
             MPC_TICK(TK_SOLVE)
         }
         // ---- PF: step length to the boundary ----
