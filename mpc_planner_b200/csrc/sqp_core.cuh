@@ -44,7 +44,11 @@
 
 namespace mpcgpu {
 
+#if defined(MPC_NT_OVERRIDE)
+constexpr int MPC_NT = MPC_NT_OVERRIDE;
+#else
 constexpr int MPC_NT = 128;  // threads per solve
+#endif
 // partials per reduced quantity: one per warp on the device (threads pre-reduce with shuffles),
 // one per thread in the host emulation
 #if defined(__CUDACC__)
@@ -75,10 +79,16 @@ struct ParamP {
 
 
 
-// NaN-propagating running max
+// NaN-propagating running max of values that are >= +0 or NaN (every caller passes fabs(.) and starts from 0): on the
+// device an unsigned integer max of the bit patterns (monotone for such values, NaNs sort above +inf)
 MPC_HD void upd_max(double &acc, double v) {
+#if defined(__CUDA_ARCH__)
+    const unsigned long long a = (unsigned long long)__double_as_longlong(acc), b = (unsigned long long)__double_as_longlong(v);
+    acc = __longlong_as_double((long long)(b > a ? b : a));
+#else
     if (acc != acc) return;
     if (v != v || v > acc) acc = v;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -355,6 +365,9 @@ struct RicIdx {
 
 // Backward factorisation: for k = N-1..0   M = H + barrier terms + [B A]' P+ [B A];
 //   Luu = chol(Muu);  Lxu = Mxu Luu^-T;  P = Mxx - Lxu Lxu';  PC(k+1) = P_{k+1} c_k.
+// The backward VECTOR sweep for the gradient currently in GT (the predictor right-hand side) rides along: its ~45
+// FP64 operations per stage are independent of the matrix recursion and fill that chain's latency bubbles, which is
+// cheaper than a separate pass over the horizon (riccati_solve<CFG, false> then only runs the forward sweep).
 template <class CFG>
 MPC_DEV void riccati_factor(double *sm) {
     typedef SL<CFG> S;
@@ -364,13 +377,18 @@ MPC_DEV void riccati_factor(double *sm) {
     const int serial_tid = (int)sm[S::W_BASE + S::W_STID];
     MPC_PHASE
     if (tid == serial_tid) {
-        double Pn[S::NPP];
+        double Pn[S::NPP], pv[NX];
 #pragma unroll
         for (int e = 0; e < S::NPP; e++) Pn[e] = sm[N * S::STRIDE + S::P + e];
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+            pv[i] = sm[N * S::STRIDE + S::GT + NU + i];  // terminal: pv_N = gt_N
+            sm[N * S::STRIDE + S::PV + i] = pv[i];
+        }
         for (int k = N - 1; k >= 0; k--) {
             double *st = sm + k * S::STRIDE;
             double *stn = st + S::STRIDE;
-            double B[NX][NU], E[NX][NE], PB[NX][NU], PE[NX][NE];
+            double B[NX][NU], E[NX][NE], PB[NX][NU], PE[NX][NE], qv[NX];
 #pragma unroll
             for (int l = 0; l < NX; l++) {
 #pragma unroll
@@ -397,6 +415,14 @@ MPC_DEV void riccati_factor(double *sm) {
                     pc += plm * st[S::C + m];
                 }
                 stn[S::PC + l] = pc;
+                qv[l] = pv[l] + pc;  // vector sweep: q = pv+ + P+ c
+            }
+            // vector sweep: m = gt + [B A]' q
+            double mv0 = st[S::GT + 0], mv1 = st[S::GT + 1];
+#pragma unroll
+            for (int l = 0; l < NX; l++) {
+                if (R::bnz(l, 0)) mv0 += B[l][0] * qv[l];
+                if (R::bnz(l, 1)) mv1 += B[l][1] * qv[l];
             }
             // M_uu
             double m00 = st[S::H + tri(0, 0)] + st[S::GD + 0], m10 = st[S::H + tri(1, 0)], m11 = st[S::H + tri(1, 1)] + st[S::GD + 1];
@@ -412,6 +438,10 @@ MPC_DEV void riccati_factor(double *sm) {
             st[S::LUU] = il00;
             st[S::LUU + 1] = l10;
             st[S::LUU + 2] = il11;
+            const double yv0 = mv0 * il00;  // vector sweep: y = L_uu^-1 m_u
+            const double yv1 = (mv1 - l10 * yv0) * il11;
+            st[S::YV] = yv0;
+            st[S::YV + 1] = yv1;
             // M_xu = H_xu + A' P B = H_xu + PB + E' PB (rows psi, v only);  L_xu = M_xu L_uu^-T
             double Lx[NX][NU];
 #pragma unroll
@@ -429,6 +459,15 @@ MPC_DEV void riccati_factor(double *sm) {
                 Lx[i][1] = (mx1 - Lx[i][0] * l10) * il11;
                 st[S::LXU + i * NU] = Lx[i][0];
                 st[S::LXU + i * NU + 1] = Lx[i][1];
+                // vector sweep: pv_i = m_x,i - L_xu,i y,  m_x = gt_x + A' q,  A = I + E
+                double mx = st[S::GT + NU + i] + qv[i];
+                if (R::eidx(i) >= 0) {
+#pragma unroll
+                    for (int l = 0; l < NX; l++)
+                        if (R::enz(l, R::eidx(i) >= 0 ? R::eidx(i) : 0)) mx += E[l][R::eidx(i) >= 0 ? R::eidx(i) : 0] * qv[l];
+                }
+                pv[i] = mx - Lx[i][0] * yv0 - Lx[i][1] * yv1;
+                st[S::PV + i] = pv[i];
             }
             // M_xx = H_xx + barrier + A' P A,  A' P A = P + PE Sel + Sel' PE' + Sel' (E' PE) Sel;  P = M_xx - L_xu L_xu'
             double Pk[S::NPP];
@@ -729,8 +768,8 @@ MPC_DEV void riccati_factor_lanes(double *sm) {
 }
 
 // Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PIN.
-template <class CFG, bool BACKWARD = true>
-MPC_DEV void riccati_solve(double *sm) {
+template <class CFG>
+MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
     typedef SL<CFG> S;
     typedef RicIdx<CFG> R;
     constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
@@ -1062,9 +1101,14 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
             double *st = sm + k * S::STRIDE;
             const double lb = W[S::W_LB + i], ub = W[S::W_UB + i];
             const double z = st[S::Z + i], v = st[S::DZ + i], vn = st[S::DZN + i];
-            // rows are relaxed by qp_relax (see mpcgpu.h): an interior exists even for rows pinned at their bound
-            if (lb > -1e10) row_body<CFG, MODE>(st, i, z - lb + v + L.qp_relax, z - lb + vn + L.qp_relax, c);
-            if (ub < 1e10) row_body<CFG, MODE>(st, NZ + i, ub - z - v + L.qp_relax, ub - z - vn + L.qp_relax, c);
+            // rows are relaxed by qp_relax (see mpcgpu.h): an interior exists even for rows pinned at their bound.
+            // One copy of the row body for both sides (run-time loop): lower z - lb + v, upper ub - z - v = -(z - ub + v)
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                const double bnd = side ? ub : lb, sgn = side ? -1.0 : 1.0;
+                const bool active = side ? (ub < 1e10) : (lb > -1e10);
+                if (active) row_body<CFG, MODE>(st, side * NZ + i, sgn * (z - bnd + v) + L.qp_relax, sgn * (z - bnd + vn) + L.qp_relax, c);
+            }
         }
         // general rows of stages 1..N-1
         for (int it = tid; it < (N - 1) * NH; it += NT) {
@@ -1175,15 +1219,13 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
         if (rs < L.qp_tol && re < L.qp_tol && ri < L.qp_tol && rc < L.qp_tol) { status = 0; break; }
         if (iter >= L.qp_iter_max) { status = 2; break; }
 
-#if defined(MPC_RICCATI_SERIAL)
-        riccati_factor<CFG>(sm);
-        MPC_TICK(TK_FACTOR)
-        riccati_solve<CFG, true>(sm);
+#if defined(MPC_RICCATI_LANES)
+        riccati_factor_lanes<CFG>(sm);  // measured alternative: same throughput, 5 % more solo latency
 #else
-        riccati_factor_lanes<CFG>(sm);  // + backward sweep of the predictor right-hand side
-        MPC_TICK(TK_FACTOR)
-        riccati_solve<CFG, false>(sm);
+        riccati_factor<CFG>(sm);        // + backward sweep of the predictor right-hand side
 #endif
+        MPC_TICK(TK_FACTOR)
+        riccati_solve<CFG>(sm, false);
         MPC_TICK(TK_SOLVE)
         sigma_mu = 0.0;
         if (nc > 0) {
@@ -1209,7 +1251,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
             // ---- PE: corrector gradient and solve ----
             stage_accumulate<CFG, 1>(L, sm, sigma_mu);
             MPC_TICK(TK_ACC1)
-            riccati_solve<CFG, true>(sm);
+            riccati_solve<CFG>(sm, true);
             MPC_TICK(TK_SOLVE)
         }
         // ---- PF: step length to the boundary ----

@@ -4,6 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mpc_planner_b200 import binding, problem as pb, scenes
 
+if os.environ.get("MPC_LIB"):
+    binding.LIB_PATH = os.path.abspath(os.environ["MPC_LIB"])
 spec = pb.config_tmpc()
 base = scenes.make_scene_batch(spec, 1, 8, seed=1)
 for P in [int(a) for a in sys.argv[1:]] or [8]:

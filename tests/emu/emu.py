@@ -20,6 +20,15 @@ def build_generated(registry_header, out):
     return out
 
 
+def build_variant(defines, out):
+    """Host emulation compiled with extra -D flags (e.g. MPC_RICCATI_LANES: the lane-cooperative factorisation)."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include")] + ["-D" + d for d in defines]
+                          + ["-o", out, os.path.join(_HERE, "emu.cpp")])
+    return out
+
+
 def build(force=False):
     srcs = [os.path.join(_HERE, "emu.cpp")] + [
         os.path.join(_ROOT, "mpc_planner_b200", "csrc", f) for f in ("sqp_core.cuh", "stage_functions.cuh", "registry.cuh")
