@@ -328,18 +328,46 @@ MPC_HD void assemble_stage(const Layout &L, double *st) {
     double g[NZ];
 #pragma unroll
     for (int i = 0; i < NZ; i++) g[i] = st[S::LS_GC + i];
-    // Jacobi work space: M in the (dead between QPs) T/TINV/CORR rows area, V in the IPM work area
-    static_assert(3 * S::NROW >= NZ * NZ && S::RAW - S::WK >= NZ * NZ, "MIRROR work space");
-    // block structure of the MPCC Hessian: {a, w, psi, v} and {x, y, spline (, slack)} decouple unless the disc is
-    // offset from the robot centre (then d2h/dx dpsi != 0) -- checked at run time inside mirror_block
-    constexpr bool BLOCKS = (CFG::OBJ == MPCGPU_OBJ_CONTOURING);
-    const int ia[4] = {CFG::IA, CFG::IW, CFG::IPSI, CFG::IV};
-    const int ib[4] = {CFG::IX, CFG::IY, CFG::IS, CFG::HAS_SLACK ? CFG::ISLACK : 0};
-    mirror_block<NZ, (BLOCKS ? 4 : 0)>(Hp, L.reg_epsilon, st + S::T, st + S::WK, ia, ib);
 #pragma unroll
     for (int i = 0; i < S::NHP; i++) st[S::H + i] = Hp[i];
 #pragma unroll
     for (int i = 0; i < NZ; i++) st[S::GR + i] = g[i];
+    {   // block structure flag for mirror_stage (DZN is dead between QPs and outside the linearisation scratch)
+        const int ia[4] = {CFG::IA, CFG::IW, CFG::IPSI, CFG::IV};
+        const int ib[4] = {CFG::IX, CFG::IY, CFG::IS, CFG::HAS_SLACK ? CFG::ISLACK : 0};
+        bool decoupled = (CFG::OBJ == MPCGPU_OBJ_CONTOURING);
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < NZ - 4; b++) decoupled = decoupled && (Hp[trisym(ia[a], ib[b])] == 0.0);
+        static_assert(S::DZN >= S::LS_END, "flag must not overlap the linearisation scratch");
+        st[S::DZN] = decoupled ? 1.0 : 0.0;
+    }
+}
+
+// MIRROR of the assembled stage Hessian st[H] (in place), thread = (stage, part).  For the MPCC objective with a centred
+// disc the block is exactly block diagonal over {a, w, psi, v} and {x, y, spline (, slack)} (checked at run time): the two
+// blocks are then regularised by two different threads (part 0 / part 1) -- the eigen-decomposition of a block-diagonal
+// matrix is the union of its blocks' -- else part 0 runs the general path on the whole block.
+template <class CFG>
+MPC_HD void mirror_stage(const Layout &L, double *st, int part) {
+    typedef SL<CFG> S;
+    constexpr int NZ = CFG::NZ;
+    // Jacobi work space of the general path: M in the (dead between QPs) T/TINV/CORR rows area, V in the IPM work area
+    static_assert(3 * S::NROW >= NZ * NZ && S::RAW - S::WK >= NZ * NZ, "MIRROR work space");
+    constexpr bool BLOCKS = (CFG::OBJ == MPCGPU_OBJ_CONTOURING);
+    constexpr int NA = 4, NB = NZ - NA;
+    const int ia[4] = {CFG::IA, CFG::IW, CFG::IPSI, CFG::IV};
+    const int ib[4] = {CFG::IX, CFG::IY, CFG::IS, CFG::HAS_SLACK ? CFG::ISLACK : 0};
+    double *Hp = st + S::H;
+    if (BLOCKS) {
+        if (st[S::DZN] != 0.0) {  // written by assemble_stage: exactly block diagonal
+            if (part == 0) mirror_subblock<NA>(Hp, L.reg_epsilon, ia);
+            else mirror_subblock<NB>(Hp, L.reg_epsilon, ib);
+            return;
+        }
+    }
+    if (part == 0) mirror_block<NZ, 0>(Hp, L.reg_epsilon, st + S::T, st + S::WK, ia, ib);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -432,9 +460,12 @@ MPC_DEV void riccati_factor(double *sm) {
                 if (R::bnz(l, 1)) m10 += B[l][1] * PB[l][0];
                 if (R::bnz(l, 1)) m11 += B[l][1] * PB[l][1];
             }
+            // the two reciprocal square roots are independent: 1/l11 = rsqrt(m11 - m10^2/m00) = sqrt(m00) rsqrt(m00 m11 - m10^2)
+            // (one rsqrt latency, ~75 cycles, off the per-stage critical path)
             const double il00 = mpc_rsqrt(m00);
+            const double rdet = mpc_rsqrt(m11 * m00 - m10 * m10);
             const double l10 = m10 * il00;
-            const double il11 = mpc_rsqrt(m11 - l10 * l10);
+            const double il11 = rdet * (m00 * il00);
             st[S::LUU] = il00;
             st[S::LUU + 1] = l10;
             st[S::LUU + 2] = il11;
@@ -1343,9 +1374,16 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         MPC_PHASE_END
         MPC_TICK(TK_LIN)
         MPC_PHASE
-        {   // stages spread over the warps (lanes 0..ceil(N/4)-1 of each): MIRROR's Jacobi sweeps diverge per stage
+        {   // stages spread over the warps (lanes 0..ceil(N/4)-1 of each)
             const int k = (tid & 31) * (NT / 32) + (tid >> 5);
             if ((tid & 31) < (N + NT / 32 - 1) / (NT / 32) && k < N) assemble_stage<CFG>(L, sm + k * S::STRIDE);
+        }
+        MPC_PHASE_END
+        MPC_PHASE
+        {   // MIRROR: (stage, part) items spread over the warps: the Jacobi sweeps diverge per item
+            constexpr int NI = 2 * N, NW = NT / 32;
+            const int it = (tid & 31) * NW + (tid >> 5);
+            if ((tid & 31) < (NI + NW - 1) / NW && it < NI) mirror_stage<CFG>(L, sm + (it >> 1) * S::STRIDE, it & 1);
         }
         MPC_PHASE_END
         MPC_TICK(TK_ASM)
