@@ -180,6 +180,14 @@ int mpcgpu_set_state(mpcgpu_handle h, int first, int count, const double *state)
  * (or -1).  group = 0 (default) treats the whole batch as one group. */
 int mpcgpu_set_group(mpcgpu_handle h, int group);
 
+/* Solver::solve()'s timeout (mpc_planner_solver/src/acados_solver_interface.cpp:91-117, `_params.solver_timeout`,
+ * set per control step at mpc_planner/src/planner.cpp:118 and guidance_constraints.cpp:258,333): after each SQP-RTI
+ * iteration a solve stops iterating once (time since the start of THIS solve) + (its average iteration time) >= seconds,
+ * then completes as usual (trajectories, cost, exit code; mpcgpu_info.sqp_iter tells how many iterations ran).  Time is
+ * read on the device (%globaltimer) per solve; it applies to every following solve call on the handle.
+ * seconds <= 0 disables the check (default) -- note that the reference with solver_timeout = 0 stops after one iteration. */
+int mpcgpu_set_timeout(mpcgpu_handle h, double seconds);
+
 /* Pinned host staging buffers for the host path (optional; plain malloc'd memory also works). */
 int mpcgpu_host_alloc(void **ptr, unsigned long long bytes);
 int mpcgpu_host_free(void *ptr);

@@ -20,7 +20,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 # every symbol include/mpcgpu.h declares
 EXPORTED_SYMBOLS = [
     "mpcgpu_version", "mpcgpu_strerror", "mpcgpu_device_count", "mpcgpu_problem_supported", "mpcgpu_create", "mpcgpu_destroy",
-    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_set_group",
+    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_set_group", "mpcgpu_set_timeout",
     "mpcgpu_set_stateful", "mpcgpu_state_size", "mpcgpu_reset_state", "mpcgpu_get_state", "mpcgpu_set_state", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
     "mpcgpu_set_timing", "mpcgpu_kernel_ms", "mpcgpu_eval_stage", "mpcgpu_measure_fp64_gflops",
 ]
@@ -52,6 +52,7 @@ def load_library(path: str | None = None):
                                            ctypes.POINTER(SolveInfo), _ip]
     lib.mpcgpu_set_group.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.mpcgpu_set_stateful.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.mpcgpu_set_timeout.argtypes = [ctypes.c_void_p, ctypes.c_double]
     lib.mpcgpu_state_size.argtypes = [ctypes.c_void_p]
     lib.mpcgpu_reset_state.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     lib.mpcgpu_get_state.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp]
@@ -109,6 +110,11 @@ class BatchSolver:
         """Guesses per control step: `best` becomes one winner index per group of consecutive solves."""
         _check(self.lib.mpcgpu_set_group(self.handle, int(group)), "mpcgpu_set_group")
         self.group = int(group)
+
+    def set_timeout(self, seconds: float):
+        """`_params.solver_timeout` (acados_solver_interface.cpp:91-117): per-solve time budget checked on the device
+        after every SQP-RTI iteration; <= 0 disables it."""
+        _check(self.lib.mpcgpu_set_timeout(self.handle, float(seconds)), "mpcgpu_set_timeout")
 
     # ---- persistent NLP multipliers per solve slot (Solver::operator= keeps the destination's acados memory) ----
     def set_stateful(self, enable=True):

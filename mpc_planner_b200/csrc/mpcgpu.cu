@@ -585,6 +585,12 @@ int mpcgpu_set_group(mpcgpu_handle h, int group) {
     return MPCGPU_OK;
 }
 
+int mpcgpu_set_timeout(mpcgpu_handle h, double seconds) {
+    if (!h || seconds != seconds) return MPCGPU_ERR_ARG;
+    h->layout.timeout_s = seconds > 0.0 ? seconds : 0.0;
+    return MPCGPU_OK;
+}
+
 long long mpcgpu_launch_count(mpcgpu_handle h) { return h ? h->launches : 0; }
 
 int mpcgpu_set_timing(mpcgpu_handle h, int enabled) {

@@ -91,6 +91,24 @@ MPC_HD void upd_max(double &acc, double v) {
 #endif
 }
 
+// Nanosecond clock for the solver timeout: %globaltimer on the device.  The host emulation uses a deterministic fake clock
+// (tests/emu: every read advances it by emu_clock_step_ns) so that the CPU suite can pin the iteration-count logic.
+#if !defined(__CUDACC__)
+extern long long g_emu_clock_ns, g_emu_clock_step_ns;
+#endif
+MPC_DEV long long mpc_clock_ns() {
+#if defined(__CUDA_ARCH__)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (long long)t;
+#elif !defined(__CUDACC__)
+    g_emu_clock_ns += g_emu_clock_step_ns;
+    return g_emu_clock_ns;
+#else
+    return 0;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Shared-memory image of one stage (offsets in doubles; odd stride => "thread = stage" accesses
 // are bank-conflict free for 8-byte words)
@@ -148,7 +166,8 @@ struct SL {
     static constexpr int W_LB = W_DX0 + NX;     // NZ lower bounds (copy of Layout, for dynamic indexing)
     static constexpr int W_UB = W_LB + NZ;      // NZ upper bounds
     static constexpr int W_STID = W_UB + NZ;    // id of the thread that runs the serial Riccati sweeps
-    static constexpr int W_MBUF = W_STID + 1;   // lane-cooperative factorisation: double-buffered staging tile (packed lower NZ x NZ)
+    static constexpr int W_TMO = W_STID + 1;    // timeout flag of the current SQP iteration
+    static constexpr int W_MBUF = W_TMO + 1;    // lane-cooperative factorisation: double-buffered staging tile (packed lower NZ x NZ)
     static constexpr int W_PROF = W_MBUF + 2 * NHP;  // 32 doubles (profiling builds)
 #if defined(MPC_PROFILE)
     static constexpr int W_SIZE = W_PROF + 32;
@@ -400,7 +419,7 @@ template <class CFG>
 MPC_DEV void riccati_factor(double *sm) {
     typedef SL<CFG> S;
     typedef RicIdx<CFG> R;
-    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
+    constexpr int N = CFG::N, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
     static_assert(NU == 2, "input block is factorised in closed form for nu = 2");
     const int serial_tid = (int)sm[S::W_BASE + S::W_STID];
     MPC_PHASE
@@ -803,7 +822,7 @@ template <class CFG>
 MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
     typedef SL<CFG> S;
     typedef RicIdx<CFG> R;
-    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
+    constexpr int N = CFG::N, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
     double *W = sm + S::W_BASE;
     const int serial_tid = (int)W[S::W_STID];
     MPC_PHASE
@@ -1176,11 +1195,11 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
 template <class CFG>
 MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, double *res_out) {
     typedef SL<CFG> S;
-    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NROW = CFG::NROW, NT = MPC_NT;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NT = MPC_NT;
     double *W = sm + S::W_BASE;
     double *mpc_prof = W + S::W_PROF;
     (void)mpc_prof;
-    const double T_MIN = 1e-10, LAM_MIN = 1e-16, ALPHA_MIN = 1e-12;
+    const double ALPHA_MIN = 1e-12;
     // number of inequality rows in the QP (uniform)
     int nc = 0;
     for (int i = 0; i < NZ; i++) {
@@ -1348,7 +1367,16 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         W[S::W_UB + tid] = L.upper_bound[tid];
     }
     if (tid == NZ) W[S::W_STID] = (double)serial_tid;
+    if (tid == NZ + 1) W[S::W_TMO] = 0.0;
     MPC_PHASE_END
+    // Solver::solve()'s timeout (acados_solver_interface.cpp:91-117): stop iterating once the time since the start of the
+    // solve plus the average iteration time reaches the budget.  Only thread 0 keeps the clocks; the decision travels
+    // through shared memory with the barrier that ends the step phase.
+    long long t_solve0 = 0, t_iter0 = 0, t_iters = 0;
+    if (L.timeout_s > 0.0) {
+        t_solve0 = mpc_clock_ns();
+        t_iter0 = t_solve0;
+    }
 #if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
     if (threadIdx.x == 0) {
         for (int i = 0; i < 32; i++) mpc_prof[i] = 0.0;
@@ -1405,9 +1433,17 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
                 else iterates[(sq * (N + 1) + k) * NZ + ((i >= NU) ? i - NU : NX + i)] = (i >= NU) ? zi : 0.0;
             }
         }
+        if (tid == 0 && L.timeout_s > 0.0) {
+            const long long now = mpc_clock_ns();
+            t_iters += now - t_iter0;
+            t_iter0 = now;
+            const double avg = (double)t_iters / (double)(sq + 1), elapsed = (double)(now - t_solve0);
+            W[S::W_TMO] = (elapsed + avg >= L.timeout_s * 1e9) ? 1.0 : 0.0;
+        }
         MPC_PHASE_END
         MPC_TICK(TK_STEP)
         if (qp_status != 0) break;  // Q4: the reference loop stops on any non-zero qp_status
+        if (W[S::W_TMO] != 0.0) break;  // out of time (:112-116)
     }
 
     // completeOneIteration (acados_solver_interface.cpp:162-204): cost, trajectories, res_eq

@@ -105,6 +105,8 @@ int Solver::solveOneIteration() {  // :145-160
     mpcgpu_handle h = handle(1);
     if (!persistent_multipliers) std::fill(_nlp_multipliers.begin(), _nlp_multipliers.end(), 0.0);
     int rc = mpcgpu_set_state(h, 0, 1, _nlp_multipliers.data());
+    // :91,112 the RTI loop stops when the budget is used up; _params.solver_timeout <= 0 (never set) leaves it unbounded
+    if (rc == 0) rc = mpcgpu_set_timeout(h, _params.solver_timeout);
     if (rc == 0)
         rc = mpcgpu_solve_host(h, 1, _params.xinit.data(), _loaded_x0.data(), _params.all_parameters.data(), xtraj.data(), utraj.data(),
                                &info, nullptr);
@@ -139,6 +141,11 @@ int Solver::solveBatch(const std::vector<Solver *> &solvers, std::vector<int> &e
         for (int i = 0; i < P; i++) std::copy(solvers[i]->_nlp_multipliers.begin(), solvers[i]->_nlp_multipliers.end(), mult.begin() + i * ns);
     mpcgpu_handle h = lead->handle(P);
     int rc = mpcgpu_set_state(h, 0, P, mult.data());
+    {   // guidance_constraints.cpp:333 gives every local planner the same budget; one launch: the smallest, unbounded if any is unset
+        double tmo = solvers[0]->_params.solver_timeout;
+        for (const Solver *sv : solvers) tmo = (sv->_params.solver_timeout <= 0.0 || tmo <= 0.0) ? 0.0 : std::min(tmo, sv->_params.solver_timeout);
+        if (rc == 0) rc = mpcgpu_set_timeout(h, tmo);
+    }
     if (rc == 0) rc = mpcgpu_solve_host(h, P, xinit.data(), x0.data(), par.data(), xtraj.data(), utraj.data(), info.data(), &best);
     if (rc == 0) rc = mpcgpu_get_state(h, 0, P, mult.data());
     if (rc != 0) throw std::runtime_error(std::string("mpcgpu_solve_host: ") + mpcgpu_strerror(rc));

@@ -173,6 +173,16 @@ static void test_gpu(const char *in_path, const char *out_path) {
     std::fwrite(&exit_second, sizeof(int), 1, o);
     std::fwrite(&single._info.pobj, sizeof(double), 1, o);
     std::fwrite(single._output.xtraj.data(), sizeof(double), single._output.xtraj.size(), o);
+    // _params.solver_timeout (acados_solver_interface.cpp:91-117): a budget no iteration fits in -> one RTI iteration
+    single = *solvers[0];
+    single._params.solver_timeout = 1e-9;
+    single.loadWarmstart();
+    (void)single.solve();
+    CHECK(single._info.sqp_iter == 1);
+    single._params.solver_timeout = 10.0;
+    single.loadWarmstart();
+    (void)single.solve();
+    CHECK(single._info.sqp_iter > 1);
     single.reset();
     for (double v : single.nlpMultipliers()) CHECK(v == 0.0);
     std::fclose(o);

@@ -51,6 +51,13 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_dp)
 
 
+def set_timeout(timeout_s, step_ns, library=None):
+    """Fake clock of the emulation (csrc/sqp_core.cuh mpc_clock_ns): every read advances by step_ns."""
+    L = ctypes.CDLL(library) if library else lib()
+    L.emu_set_timeout.argtypes = [ctypes.c_double, ctypes.c_longlong]
+    L.emu_set_timeout(float(timeout_s), int(step_ns))
+
+
 def eval_stage(desc, z, p, lam=None, pi=None):
     nz, nx, nh = desc.nx + desc.nu, desc.nx, desc.nh
     z = np.ascontiguousarray(z, float).reshape(-1, nz)

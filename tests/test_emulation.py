@@ -73,6 +73,27 @@ def test_lane_cooperative_factorisation_variant_matches_oracle(tmp_path):
         assert n_ok >= 1
 
 
+def test_solver_timeout_iteration_count_logic():
+    """Solver::solve()'s timeout (acados_solver_interface.cpp:91-117) as restated in csrc/sqp_core.cuh: stop after iteration
+    i once elapsed + average iteration time >= budget.  The emulation's clock advances 1 ms per read, so: start = 1 ms,
+    after iteration i: elapsed = i ms, average = 1 ms."""
+    import dataclasses
+
+    spec = SPECS["cfg2"]
+    b = scenes.make_scene_batch(spec, 1, 4, seed=31)
+    try:
+        for budget_s, expect in ((1.0, 10), (0.0101, 10), (0.0035, 3), (0.0005, 1)):
+            emu.set_timeout(budget_s, 1_000_000)
+            xt, ut, info = emu.solve_batch(spec, b["xinit"], b["x0"], b["params"])
+            assert [i["sqp_iter"] for i in info] == [expect] * 4, (budget_s, info)
+            if expect == 3:  # a timed-out solve equals the plain solve with n_sqp = 3 (oracle)
+                oxt, out, oinfo = oracle.solve_batch(dataclasses.replace(spec, n_sqp=3), b["xinit"], b["x0"], b["params"])
+                np.testing.assert_allclose(xt, oxt, rtol=1e-6, atol=1e-6)
+                assert [i["exit_code"] for i in info] == [i["exit_code"] for i in oinfo]
+    finally:
+        emu.set_timeout(0.0, 0)
+
+
 def test_scene_generator_invariants():
     spec = pb.config_tmpc()
     b = scenes.make_scene_batch(spec, 2, 8, seed=4)

@@ -155,3 +155,34 @@ def test_scene_without_obstacles(binding):
     assert all(i["exit_code"] == 1 for i in info)
     np.testing.assert_allclose(xt, oxt, rtol=1e-6, atol=1e-6)
     solver.close()
+
+
+def test_solver_timeout_bounds_the_rti_iterations(binding):
+    """`_params.solver_timeout` (acados_solver_interface.cpp:91-117): a budget no iteration fits in stops every solve after
+    its first RTI iteration -- the result is then exactly the oracle's with n_sqp = 1; a generous budget changes nothing;
+    0 switches the check off again."""
+    import dataclasses
+
+    from oracle import oracle
+
+    spec = pb.config_tmpc()
+    b = scenes.make_scene_batch(spec, 4, 8, seed=9)
+    solver = binding.BatchSolver(spec, 32)
+    xt10, ut10, info10, _ = solver.solve(b["xinit"], b["x0"], b["params"])
+    assert all(i["sqp_iter"] == spec.n_sqp for i in info10 if i["qp_status"] == 0)
+    solver.set_timeout(1e-9)
+    xt1, ut1, info1, _ = solver.solve(b["xinit"], b["x0"], b["params"])
+    assert all(i["sqp_iter"] == 1 for i in info1)
+    spec1 = dataclasses.replace(spec, n_sqp=1)
+    oxt, out, oinfo = oracle.solve_batch(spec1, b["xinit"], b["x0"], b["params"])
+    for i in range(32):
+        assert info1[i]["exit_code"] == oinfo[i]["exit_code"] and info1[i]["qp_status"] == oinfo[i]["qp_status"]
+    np.testing.assert_allclose(xt1, oxt, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ut1, out, rtol=1e-6, atol=1e-6)
+    solver.set_timeout(10.0)
+    xt, ut, info, _ = solver.solve(b["xinit"], b["x0"], b["params"])
+    assert np.array_equal(xt, xt10) and np.array_equal(ut, ut10)
+    solver.set_timeout(0.0)
+    xt, ut, info, _ = solver.solve(b["xinit"], b["x0"], b["params"])
+    assert np.array_equal(xt, xt10) and [i["sqp_iter"] for i in info] == [i["sqp_iter"] for i in info10]
+    solver.close()
