@@ -16,7 +16,9 @@
 #define MPC_PLANNER_CUDA_MODULES_H
 
 #include <array>
+#include <chrono>
 #include <map>
+#include <unordered_map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -63,7 +65,14 @@ struct DynamicObstacle {
 struct RealTimeData {
     std::vector<Disc> robot_area;
     std::vector<DynamicObstacle> dynamic_obstacles;
+    // set by the caller at the start of a control step (data_types.h; the ROS wrappers do it in their loop callback); the
+    // solver timeouts are derived from it (planner.cpp:117-118, guidance_constraints.cpp:331-333).  Left at its default
+    // (epoch) the timeouts are not touched.
+    std::chrono::system_clock::time_point planning_start_time{};
 };
+// remaining time budget of this control step minus `margin`, as planner.cpp:117-118 computes it; a used-up budget becomes a
+// tiny positive one (the reference then stops after its first RTI iteration), an unset start time gives 0 (= unbounded)
+double remainingPlanningTime(const RealTimeData &data, double planning_time, double margin);
 // the reference path as the contouring module consumes it: cubic segments in arc length
 // (what RosTools::Spline2D::getParameters / getSegmentStart return, contouring.cpp:100-123)
 struct PathSegment {
@@ -88,6 +97,9 @@ struct Config {
     double robot_radius{0.325}, obstacle_radius{0.4}, risk{0.05};
     int n_discs{1}, max_obstacles{8}, num_segments{5}, add_halfspaces{0}, decomp_max_constraints{12};
     bool use_tmpcpp{true}, enable_constraints{true};
+    bool warmstart_with_mpc_solution{false};   // t-mpc/warmstart_with_mpc_solution (settings.yaml:68)
+    bool shift_previous_solution_forward{true};
+    double control_frequency{20.};             // settings.yaml:7
     double selection_weight_consistency{1.0};
     int n_paths{4};  // guidance_planner n_paths: guided planners (T-MPC++ adds the non-guided one)
 };
@@ -204,6 +216,7 @@ class GuidanceConstraintsT : public ControllerModule {
     struct LocalPlanner {
         int id;
         bool is_original_planner, disabled{true};
+        bool taken{false}, existing_guidance{false};  // guidance_constraints.h:97-98
         std::shared_ptr<Solver> local_solver;
         std::unique_ptr<LinearizedConstraints> guidance_constraints;
         std::unique_ptr<SafetyConstraints> safety_constraints;
@@ -218,10 +231,13 @@ class GuidanceConstraintsT : public ControllerModule {
     std::vector<LocalPlanner *> prepare(State &state, const RealTimeData &data, ModuleData &module_data);
     int optimize(State &state, const RealTimeData &data, ModuleData &module_data) override;
     int best_planner_index() const { return best_planner_index_; }
+    const std::unordered_map<int, int> &homotopyClassToPlanner() const { return _map_homotopy_class_to_planner; }
     std::vector<LocalPlanner> planners_;
 
   private:
     void initializeSolverWithGuidance(LocalPlanner &planner);
+    void mapGuidanceTrajectoriesToPlanners();  // :192-250
+    std::unordered_map<int, int> _map_homotopy_class_to_planner;
     int FindBestPlanner();
     std::vector<GuidanceTrajectory> _guidance;
     RealTimeData empty_data_;

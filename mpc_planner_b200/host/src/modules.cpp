@@ -305,6 +305,13 @@ void DecompConstraints::setParameters(const RealTimeData &data, const ModuleData
     }
 }
 #endif  // DECOMP
+double remainingPlanningTime(const RealTimeData &data, double planning_time, double margin) {
+    if (data.planning_start_time == std::chrono::system_clock::time_point{}) return 0.0;
+    const std::chrono::duration<double> used_time = std::chrono::system_clock::now() - data.planning_start_time;
+    const double t = planning_time - used_time.count() - margin;
+    return t > 0.0 ? t : 1e-9;
+}
+
 #if defined(MPC_PLANNER_HAS_LINEAR) && defined(MPC_PLANNER_HAS_ELLIPSOID)
 // ---- GuidanceConstraints (guidance_constraints.cpp:17-57, 264-434) ----
 template <class SC>
@@ -346,9 +353,39 @@ int GuidanceConstraintsT<SC>::FindBestPlanner() {  // :416-434
     return best_index;
 }
 template <class SC>
+void GuidanceConstraintsT<SC>::mapGuidanceTrajectoriesToPlanners() {  // :192-250
+    // keep a guidance trajectory on the planner that optimised its homotopy class last time, so that this planner's own
+    // previous solution (and multipliers) remain a valid initialisation
+    std::vector<int> remaining_trajectories;
+    for (auto &planner : planners_) planner.taken = planner.existing_guidance = false;
+    _map_homotopy_class_to_planner.clear();
+    for (int i = 0; i < (int)_guidance.size(); i++) {
+        const int homotopy_class = _guidance[i].topology_class;
+        bool planner_found = false;
+        for (size_t p = 0; p < planners_.size(); p++) {
+            if (planners_[p].result.guidance_ID == homotopy_class && !planners_[p].taken) {
+                _map_homotopy_class_to_planner[i] = (int)p;
+                planners_[p].taken = planners_[p].existing_guidance = true;
+                planner_found = true;
+                break;
+            }
+        }
+        if (!planner_found) remaining_trajectories.push_back(i);
+    }
+    for (int i : remaining_trajectories)  // as written in the reference (no break): the last free planner wins, all get marked
+        for (size_t p = 0; p < planners_.size(); p++)
+            if (!planners_[p].taken) {
+                _map_homotopy_class_to_planner[i] = (int)p;
+                planners_[p].taken = true;
+                planners_[p].existing_guidance = false;
+            }
+}
+
+template <class SC>
 std::vector<typename GuidanceConstraintsT<SC>::LocalPlanner *> GuidanceConstraintsT<SC>::prepare(State &state, const RealTimeData &data,
                                                                                                  ModuleData &module_data) {
     std::vector<LocalPlanner *> active;
+    mapGuidanceTrajectoriesToPlanners();  // :108 (uses the previous control step's results, before they are reset below)
     // what the reference does inside `#pragma omp parallel for` per planner up to solver->solve() (:279-337)
     for (auto &planner : planners_) {
         planner.result = SolverResult();
@@ -363,7 +400,10 @@ std::vector<typename GuidanceConstraintsT<SC>::LocalPlanner *> GuidanceConstrain
             planner.guidance_constraints->update(state, empty_data_, module_data);
             planner.safety_constraints->update(state, data, module_data);
         } else {
-            initializeSolverWithGuidance(planner);
+            if (CONFIG().warmstart_with_mpc_solution && planner.existing_guidance)  // :310-313
+                planner.local_solver->initializeWarmstart(state, CONFIG().shift_previous_solution_forward);
+            else
+                initializeSolverWithGuidance(planner);
             planner.guidance_constraints->update(state, data, module_data);  // linearisation of the topology constraints
             planner.safety_constraints->update(state, data, module_data);    // collision avoidance constraints
         }
@@ -371,6 +411,8 @@ std::vector<typename GuidanceConstraintsT<SC>::LocalPlanner *> GuidanceConstrain
             planner.guidance_constraints->setParameters(planner.is_original_planner ? empty_data_ : data, module_data, k);
             planner.safety_constraints->setParameters(data, module_data, k);
         }
+        // timeout: planning time - used time - time necessary afterwards (:331-333)
+        planner.local_solver->_params.solver_timeout = remainingPlanningTime(data, 1. / CONFIG().control_frequency, 0.006);
         planner.local_solver->loadWarmstart();
         active.push_back(&planner);
     }

@@ -66,6 +66,7 @@ PlannerOutput Planner::solveMPC(State &state, RealTimeData &data) {  // :37-158
     _warmstart = Trajectory();
     for (int k = 0; k < _solver->N; k++) _warmstart.add(_solver->getEgoPrediction(k, "x"), _solver->getEgoPrediction(k, "y"));
     _solver->loadWarmstart();  // :115
+    _solver->_params.solver_timeout = remainingPlanningTime(data, 1. / CONFIG().control_frequency, 0.006);  // :117-118
 
     int exit_flag = EXIT_CODE_NOT_OPTIMIZED_YET;  // :125-133
     for (auto &module : _modules) {

@@ -3,6 +3,7 @@
 // GuidanceConstraints::optimize.   The scene comes from a binary file written by tests/test_host_cpp.py; every
 // planner's packed inputs (and, in "gpu" mode, results) are written back for cross-checking against the oracle.
 //   usage: test_modules pack|gpu <scene.bin> <out.bin>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -118,6 +119,42 @@ int main(int argc, char **argv) {
     std::fwrite(solver->_output.xtraj.data(), sizeof(double), solver->_output.xtraj.size(), o);
     wd(solver->_info.pobj);
     std::fclose(o);
+    if (mode == "pack") {
+        // ---- planner <-> homotopy class mapping and timeouts of the NEXT control step (guidance_constraints.cpp:192-250,
+        // 310-313, 331-333): pretend the previous step's planners 0..3 optimised classes 7, 5, 9, 5 ----
+        auto check = [](bool ok, int line) {
+            if (!ok) {
+                std::fprintf(stderr, "check failed at line %d\n", line);
+                std::exit(1);
+            }
+        };
+        // pretend the previous step's planners 0..2 optimised classes 7, 5, 5
+        const int prev[3] = {7, 5, 5};
+        for (int p = 0; p < 3 && p < (int)guidance_module.planners_.size(); p++) guidance_module.planners_[p].result.guidance_ID = prev[p];
+        if (n_guid >= 2 && guidance_module.planners_.size() >= 3) {
+            guidance[0].topology_class = 5;   // -> planner 1 (the first planner that solved class 5): an "existing" guidance
+            guidance[1].topology_class = 11;  // new class: the free planners are handed out as the reference's loop does
+            guidance_module.setGuidanceTrajectories(guidance);
+            check(data.planning_start_time == std::chrono::system_clock::time_point{}, __LINE__);
+            guidance_module.prepare(state, data, module_data);
+            const auto &map = guidance_module.homotopyClassToPlanner();
+            check(map.at(0) == 1 && guidance_module.planners_[1].existing_guidance, __LINE__);
+            check(map.count(1) == 1 && map.at(1) == (int)guidance_module.planners_.size() - 1, __LINE__);  // no `break` in :232-241
+            check(!guidance_module.planners_[0].existing_guidance && !guidance_module.planners_[map.at(1)].existing_guidance, __LINE__);
+            check(guidance_module.planners_[0].taken, __LINE__);
+            for (auto &p : guidance_module.planners_)
+                if (!p.disabled) check(p.local_solver->_params.solver_timeout == 0.0, __LINE__);  // start time unset: untouched budget
+            data.planning_start_time = std::chrono::system_clock::now();
+            guidance_module.prepare(state, data, module_data);
+            for (auto &p : guidance_module.planners_)
+                if (!p.disabled) check(p.local_solver->_params.solver_timeout > 0.0 && p.local_solver->_params.solver_timeout < 1. / CONFIG().control_frequency, __LINE__);
+            data.planning_start_time = std::chrono::system_clock::now() - std::chrono::seconds(1);  // budget used up
+            guidance_module.prepare(state, data, module_data);
+            for (auto &p : guidance_module.planners_)
+                if (!p.disabled) check(p.local_solver->_params.solver_timeout == 1e-9, __LINE__);  // -> one RTI iteration, as in the reference
+            std::printf("homotopy mapping and timeout checks passed\n");
+        }
+    }
     std::printf("test_modules %s: %zu planners, exit %d, best %d\n", mode.c_str(), active.size(), exit_code, guidance_module.best_planner_index());
     return 0;
 }

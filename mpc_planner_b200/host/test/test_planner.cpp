@@ -5,6 +5,7 @@
 // output is synthesised here (pass each relevant obstacle on the left / right).
 //   usage: test_planner cpu                     (construction + data-readiness semantics, no GPU)
 //          test_planner gpu <scene.bin> <out.bin>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -147,6 +148,7 @@ int main(int argc, char **argv) {
         }
         planner.setGuidanceTrajectories(guidance);
 
+        data.planning_start_time = std::chrono::system_clock::now();  // what the ROS wrapper's loop callback does
         PlannerOutput out = planner.solveMPC(state, data);
         double a = -3.0, w = 0.0;  // braking command when the MPC fails
         if (out.success) {

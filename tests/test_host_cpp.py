@@ -171,6 +171,7 @@ def test_module_parameter_packing_follows_the_reference(modules_exe, tmp_path):
     out = tmp_path / "out.bin"
     r = subprocess.run([modules_exe, "pack", str(scene), str(out)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+    assert "homotopy mapping and timeout checks passed" in r.stdout  # guidance_constraints.cpp:192-250, 331-333
     _, _, planners, _, _ = _read_modules_output(out, spec)
     assert [p["id"] for p in planners] == [0, 1, 2] and [p["original"] for p in planners] == [False, False, True]
     pm, N, npar, nz, nu = spec.parameter_map(), spec.N, spec.npar, spec.nz, spec.nu
