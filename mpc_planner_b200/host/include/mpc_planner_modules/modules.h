@@ -244,5 +244,51 @@ class GuidanceConstraintsT : public ControllerModule {
     int best_planner_index_{-1};
 };
 typedef GuidanceConstraintsT<EllipsoidConstraints> GuidanceConstraints;
+
+// ---- Safe Horizon MPC (mpc_planner_modules/src/scenario_constraints.cpp:17-108) ----
+// The reference's ScenarioConstraints runs `parallel_solvers` (4) local solvers, each with its own sample set, through
+// ScenarioModule::ScenarioModule of the un-vendored oscardegroot/scenario_module (sampling, halfspace construction, the
+// SH-MPC support/removal loop).  ScenarioConstraintsT keeps the reference's control flow around that module and turns the
+// `#pragma omp parallel for` over the solvers into ONE batched launch; what it needs from the module is the surface the
+// reference uses (`initialize`, `update`, `setParameters(data, k)`) plus `completeOptimize(exit_code)`, the part of the
+// module's `optimize` that follows its solve.
+// HalfspaceScenarioModule is the stand-in used here: the scenario halfspaces of every stage are handed in from outside
+// (as DecompConstraints takes its polyhedra) and written to `disc_0_scenario_constraint_<i>_{a1,a2,b}`
+// (scenario_constraints.py:26,64-94: 24 rows, always with the slack state).
+class HalfspaceScenarioModule {
+  public:
+    void initialize(std::shared_ptr<Solver> solver);
+    /** per stage k = 0..N-1 the halfspaces a1 x + a2 y <= b of this solver's sample set (more than the solver's rows: cut) */
+    void setHalfspaces(const std::vector<std::vector<Halfspace>> &per_stage) { _halfspaces = per_stage; }
+    void update(const RealTimeData &data, const ModuleData &module_data);
+    void setParameters(const RealTimeData &data, int k);
+    int completeOptimize(int exit_code) { return exit_code; }
+
+  private:
+    std::shared_ptr<Solver> _solver;
+    std::vector<std::vector<Halfspace>> _halfspaces;
+    int _n_constraints{0};
+};
+
+template <class ScenarioModule>
+class ScenarioConstraintsT : public ControllerModule {
+  public:
+    struct ScenarioSolver {
+        std::shared_ptr<Solver> solver;
+        ScenarioModule scenario_module;
+        int exit_code{0};
+        explicit ScenarioSolver(int id);
+    };
+    ScenarioConstraintsT(std::shared_ptr<Solver> solver, int parallel_solvers = 4);  // scenario_constraints/parallel_solvers
+    void update(State &state, const RealTimeData &data, ModuleData &module_data) override;
+    void setParameters(const RealTimeData &, const ModuleData &, int) override {}  // :51-56 (the local solvers carry the parameters)
+    int optimize(State &state, const RealTimeData &data, ModuleData &module_data) override;
+    int best_solver_index() const { return _best_solver; }
+    std::vector<std::unique_ptr<ScenarioSolver>> _scenario_solvers;
+
+  private:
+    int _best_solver{-1};
+};
+typedef ScenarioConstraintsT<HalfspaceScenarioModule> ScenarioConstraints;
 }  // namespace MPCPlanner
 #endif

@@ -450,4 +450,81 @@ int GuidanceConstraintsT<SC>::optimize(State &state, const RealTimeData &data, M
 }
 template class GuidanceConstraintsT<EllipsoidConstraints>;
 #endif  // LINEAR && ELLIPSOID
+
+#if defined(MPC_PLANNER_HAS_SCENARIO)
+// ---- HalfspaceScenarioModule: stand-in for the external ScenarioModule::ScenarioModule ----
+void HalfspaceScenarioModule::initialize(std::shared_ptr<Solver> solver) {
+    _solver = solver;
+    _n_constraints = 0;
+    while (_solver->hasParameter("disc_0_scenario_constraint_" + std::to_string(_n_constraints) + "_a1")) _n_constraints++;
+}
+void HalfspaceScenarioModule::update(const RealTimeData &, const ModuleData &) {}
+void HalfspaceScenarioModule::setParameters(const RealTimeData &data, int k) {
+    // dummies (1, 0, x0 + 100), as the linear modules of the reference use for k = 0 and unused rows
+    // (linearized_constraints.cpp:155-166): always satisfied, never active
+    const double dummy_b = _solver->_params.xinit[0] + 100.0;
+    if (_solver->hasParameter("ego_disc_0_offset")) _solver->setParameter(k, "ego_disc_0_offset", data.robot_area.empty() ? 0.0 : data.robot_area[0].offset);
+    for (int i = 0; i < _n_constraints; i++) {
+        const std::string base = "disc_0_scenario_constraint_" + std::to_string(i);
+        const bool have = k >= 1 && k < (int)_halfspaces.size() && i < (int)_halfspaces[k].size();
+        _solver->setParameter(k, base + "_a1", have ? _halfspaces[k][i].A[0] : 1.0);
+        _solver->setParameter(k, base + "_a2", have ? _halfspaces[k][i].A[1] : 0.0);
+        _solver->setParameter(k, base + "_b", have ? _halfspaces[k][i].b : dummy_b);
+    }
+}
+
+// ---- ScenarioConstraints (scenario_constraints.cpp:17-108) ----
+template <class SM>
+ScenarioConstraintsT<SM>::ScenarioSolver::ScenarioSolver(int id) {  // :17-21
+    solver = std::make_shared<Solver>(id);
+    scenario_module.initialize(solver);
+}
+template <class SM>
+ScenarioConstraintsT<SM>::ScenarioConstraintsT(std::shared_ptr<Solver> solver, int parallel_solvers)
+    : ControllerModule(ModuleType::CONSTRAINT, solver, "scenario_constraints") {  // :23-36
+    for (int i = 0; i < parallel_solvers; i++) _scenario_solvers.emplace_back(std::make_unique<ScenarioSolver>(i));
+}
+template <class SM>
+void ScenarioConstraintsT<SM>::update(State &, const RealTimeData &data, ModuleData &module_data) {  // :38-49
+    for (auto &solver : _scenario_solvers) {
+        *solver->solver = *_solver;  // copy the main solver, including its initial guess
+        solver->scenario_module.update(data, module_data);
+    }
+}
+template <class SM>
+int ScenarioConstraintsT<SM>::optimize(State &, const RealTimeData &data, ModuleData &) {  // :58-108
+    std::vector<Solver *> batch;
+    for (auto &solver : _scenario_solvers) {
+        // planning timeout (:69-71; margin 0.008 here, 0.006 in the other two places)
+        const double timeout = remainingPlanningTime(data, 1. / CONFIG().control_frequency, 0.008);
+        *solver->solver = *_solver;  // copy solver parameters and initial guess (:74)
+        solver->solver->_params.solver_timeout = timeout;
+        for (int k = 0; k < _solver->N; k++) solver->scenario_module.setParameters(data, k);  // :77-80
+        solver->solver->loadWarmstart();                                                     // :82
+        batch.push_back(solver->solver.get());
+    }
+    // `solver->exit_code = solver->scenario_module.optimize(data)` (:84) for all solvers: ONE batched launch, then the
+    // module's post-solve part
+    std::vector<int> exit_codes;
+    Solver::solveBatch(batch, exit_codes);
+    for (size_t i = 0; i < _scenario_solvers.size(); i++) _scenario_solvers[i]->exit_code = _scenario_solvers[i]->scenario_module.completeOptimize(exit_codes[i]);
+    // retrieve the lowest-cost solution (:88-99)
+    double lowest_cost = 1e9;
+    _best_solver = -1;
+    for (size_t i = 0; i < _scenario_solvers.size(); i++) {
+        auto &solver = _scenario_solvers[i];
+        if (solver->exit_code == 1 && solver->solver->_info.pobj < lowest_cost) {
+            lowest_cost = solver->solver->_info.pobj;
+            _best_solver = (int)i;
+        }
+    }
+    if (_best_solver < 0) return _scenario_solvers.front()->exit_code;  // no feasible solution (:100-101)
+    auto &best = _scenario_solvers[_best_solver];
+    _solver->_output = best->solver->_output;  // load the solution into the main solver (:103-105)
+    _solver->_info = best->solver->_info;
+    _solver->_params = best->solver->_params;
+    return best->exit_code;
+}
+template class ScenarioConstraintsT<HalfspaceScenarioModule>;
+#endif  // SCENARIO
 }  // namespace MPCPlanner

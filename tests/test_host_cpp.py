@@ -304,3 +304,71 @@ def test_planner_closed_loop_avoids_obstacles_and_follows_the_path(planner_exe, 
     assert lateral.max() < 3.0 and np.median(lateral) < 0.8
     assert np.all(v >= -1e-6) and np.all(v <= 3.0 + 1e-6) and np.all(np.abs(w[success == 1]) <= 0.8 + 1e-6)
     assert set(best[success == 1].astype(int)) <= {0, 1, CONFIG_N_PATHS}
+
+
+# ---- Safe Horizon MPC control flow (scenario_constraints.cpp:38-108): `parallel_solvers` local solvers as one batch ----
+@pytest.fixture(scope="module")
+def scenario_exe():
+    return build_host.build_scenario_test("cfg4")
+
+
+def test_scenario_module_packing_cpu(scenario_exe):
+    r = subprocess.run([scenario_exe, "cpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_batched_scenario_solvers_match_python_binding(scenario_exe, tmp_path):
+    """Each of the 4 local solvers copies the main solver (parameters + initial guess), gets its own scenario halfspaces and
+    is solved in the same launch; the lowest-cost feasible one is loaded into the main solver (:88-105)."""
+    from mpc_planner_b200 import binding
+
+    spec = pb.config_safe_horizon()
+    P = 4
+    b = scenes.make_scene_batch(spec, 1, P, seed=12)
+    pm, N, npar = spec.parameter_map(), spec.N, spec.npar
+    n_rows = 24
+    cols = np.array([[pm[f"disc_0_scenario_constraint_{i}_{s}"] for s in ("a1", "a2", "b")] for i in range(n_rows)])
+    par = b["params"].reshape(P, N, npar)
+    # what the reference does: every local solver starts from the MAIN solver's parameters and initial guess
+    xinit = np.tile(b["xinit"][0], (P, 1))
+    x0 = np.tile(b["x0"][0], (P, 1))
+    blocks = np.tile(par[0], (P, 1, 1))
+    blocks[:, 1:, cols.ravel()] = par[:, 1:][:, :, cols.ravel()]
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("i", P))
+        f.write(xinit[0].tobytes())
+        f.write(x0[0].tobytes())
+        f.write(par[0].tobytes())
+        f.write(struct.pack("i", n_rows))
+        for p in range(P):
+            f.write(np.ascontiguousarray(par[p][:, cols]).tobytes())  # [k][row][a1, a2, b]
+    r = subprocess.run([scenario_exe, "gpu", str(fin), str(fout)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    solver = binding.BatchSolver(spec, P)
+    xt, ut, info, best = solver.solve(xinit, x0, blocks.reshape(P, -1))
+    raw = open(fout, "rb").read()
+    cbest, cexit = struct.unpack_from("ii", raw, 0)
+    off = 8
+    nxt, nut = (N + 1) * spec.nx, N * spec.nu
+    for p in range(P):
+        (ec,) = struct.unpack_from("i", raw, off)
+        off += 4
+        (pobj,) = struct.unpack_from("d", raw, off)
+        off += 8
+        cx = np.frombuffer(raw, np.float64, nxt, off)
+        off += 8 * nxt
+        cu = np.frombuffer(raw, np.float64, nut, off)
+        off += 8 * nut
+        assert ec == info[p]["exit_code"]
+        assert np.array_equal(cx, xt[p].ravel()) and np.array_equal(cu, ut[p].ravel()) and pobj == info[p]["pobj"]
+    ok = [p for p in range(P) if info[p]["exit_code"] == 1]
+    expect = min(ok, key=lambda p: (info[p]["pobj"], p)) if ok else -1
+    assert cbest == expect == best
+    if ok:
+        main_x = np.frombuffer(raw, np.float64, nxt, off)
+        assert cexit == 1 and np.array_equal(main_x, xt[expect].ravel())
+    assert len(ok) >= 1
+    solver.close()
