@@ -192,3 +192,95 @@ def test_first_rti_step_solves_the_qp_an_independent_solver_finds():
         if checked >= 2:
             break
     assert checked >= 1
+
+
+@pytest.mark.parametrize("k_done", [1, 3])
+def test_later_rti_steps_solve_the_exact_hessian_qp_an_independent_solver_finds(k_done):
+    """RTI step k+1 with NON-zero multipliers: the oracle's step from iterate k equals the argmin of the QP an independent
+    assembly builds there -- Hessian of the Lagrangian = dt * cost Hessian + sum_j w_j Hess h_j + sum_i pi_i Hess Phi_i with the
+    multipliers the oracle holds after k steps (w = lam_hi - lam_lo; read back through the persistent-multiplier state),
+    MIRROR by an eigen-decomposition, linearised ERK4 dynamics, boxes, linearised h -- solved by scipy's SLSQP from zero.
+    This pins exact-Hessian assembly, MIRROR on indefinite blocks and the warm-started interior-point solve together."""
+    import dataclasses
+
+    from scipy.optimize import minimize
+
+    spec = pb.config_tmpc()
+    b = scenes.make_scene_batch(spec, 1, 3, seed=4)
+    d = spec.desc()
+    N, nx, nu, nz, npar, nh = spec.N, spec.nx, spec.nu, spec.nz, spec.npar, spec.nh
+    P = len(b["xinit"])
+    state = np.zeros((P, oracle.state_size(spec)))
+    xt_k, ut_k, info_k = oracle.solve_batch(dataclasses.replace(spec, n_sqp=k_done), b["xinit"], b["x0"], b["params"], state=state)
+    xt_1, ut_1, info_1 = oracle.solve_batch(dataclasses.replace(spec, n_sqp=k_done + 1), b["xinit"], b["x0"], b["params"])
+    lh, uh = map(np.array, spec.constraint_bounds())
+    lo, up = np.array(list(d.lower_bound)[:nz]), np.array(list(d.upper_bound)[:nz])
+    checked, indefinite = 0, 0
+    for i in range(P):
+        if info_k[i]["qp_status"] != 0 or info_1[i]["qp_status"] != 0:
+            continue
+        par = b["params"][i].reshape(N, npar)
+        z0 = np.zeros((N + 1, nz))
+        z0[:N, :nu], z0[:N, nu:] = ut_k[i], xt_k[i][:N]
+        xN0 = xt_k[i][N]
+        pi = state[i, : (N + 1) * nx].reshape(N + 1, nx)
+        lam = state[i, (N + 1) * nx:].reshape(N, nh)
+        w_h = np.where(np.isfinite(lh), -lam, lam)  # L += lam_hi (h - uh) + lam_lo (lh - h)
+        assert np.abs(pi).max() > 0 and lam.max() >= 0
+        ev = [oracle.eval_stage(d, z0[k], par[k], w_h[k] if k >= 1 else np.zeros(nh), pi[k + 1]) for k in range(N)]
+        H = []
+        for k in range(N):
+            Hk = spec.dt * ev[k]["cost_hess"] + ev[k]["dyn_hess"] + (ev[k]["h_hess"] if k >= 1 else 0.0)
+            Hk = 0.5 * (Hk + Hk.T)
+            wv, V = np.linalg.eigh(Hk)
+            indefinite += int(wv.min() < -spec.reg_epsilon)
+            wm = np.where(np.abs(wv) <= spec.reg_epsilon, spec.reg_epsilon, np.abs(wv))
+            H.append((V * wm) @ V.T)
+        g = [spec.dt * ev[k]["cost_grad"] for k in range(N)]
+        nvar = N * nz + nx
+
+        def split(w):
+            return w[: N * nz].reshape(N, nz), w[N * nz:]
+
+        def obj(w):
+            dz, dxN = split(w)
+            return sum(0.5 * dz[k] @ H[k] @ dz[k] + g[k] @ dz[k] for k in range(N)) + 0.5 * spec.reg_epsilon * dxN @ dxN
+
+        def obj_grad(w):
+            dz, dxN = split(w)
+            return np.concatenate([np.concatenate([H[k] @ dz[k] + g[k] for k in range(N)]), spec.reg_epsilon * dxN])
+
+        def eq(w):
+            dz, dxN = split(w)
+            out = [z0[0, nu:] + dz[0, nu:] - b["xinit"][i]]
+            for k in range(N):
+                nxt = (z0[k + 1, nu:] + dz[k + 1, nu:]) if k + 1 < N else (xN0 + dxN)
+                out.append(ev[k]["xnext"] + ev[k]["AB"] @ dz[k] - nxt)
+            return np.concatenate(out)
+
+        def ineq(w):
+            dz, _ = split(w)
+            out = []
+            for k in range(N):
+                sl = slice(0, nz) if k >= 1 else slice(0, nu)
+                out += [z0[k, sl] + dz[k, sl] - lo[sl], up[sl] - z0[k, sl] - dz[k, sl]]
+                if k >= 1:
+                    h = ev[k]["h"] + ev[k]["h_jac"] @ dz[k]
+                    out += [(h - lh)[np.isfinite(lh)], (uh - h)[np.isfinite(uh)]]
+            return np.concatenate(out)
+
+        res = minimize(obj, np.zeros(nvar), jac=obj_grad, method="SLSQP", constraints=[dict(type="eq", fun=eq), dict(type="ineq", fun=ineq)],
+                       options=dict(maxiter=1500, ftol=1e-13))
+        assert res.success, res.message
+        dz_ref, dxN_ref = split(res.x)
+        step = np.concatenate([ut_1[i], xt_1[i][:N]], axis=1) - z0[:N]
+        stepN = xt_1[i][N] - xN0
+        w_or = np.concatenate([step.ravel(), stepN])
+        assert np.abs(eq(w_or)).max() < 1e-8 and ineq(w_or).min() > -1e-6
+        assert obj(w_or) == pytest.approx(res.fun, abs=2e-5)
+        np.testing.assert_allclose(step, dz_ref, atol=5e-4)
+        np.testing.assert_allclose(stepN, dxN_ref, atol=5e-4)
+        print("qp check (step %d): obj gap %.2e, max step diff %.2e, max |step| %.2e" % (k_done + 1, obj(w_or) - res.fun, np.abs(step - dz_ref).max(), np.abs(step).max()))
+        checked += 1
+    assert checked >= 1
+    print("stage blocks with an eigenvalue below -eps (MIRROR active):", indefinite)
