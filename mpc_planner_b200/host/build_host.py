@@ -62,3 +62,17 @@ def build_scenario_test(name="cfg4", out_dir=None):
            os.path.join(HERE, "test", "test_scenario.cpp"), "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-o", exe]
     subprocess.check_call(cmd)
     return exe
+
+
+def build_packing_test(name):
+    """Parameter packing of the Gaussian / decomp modules (host/test/test_packing.cpp) for the stack `name`."""
+    spec = pb.CONFIGS[name]()
+    out_dir = os.path.join(HERE, "generated", name)
+    generate_solver(spec, out_dir)
+    exe = os.path.join(out_dir, "test_packing")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-I" + out_dir, "-I" + os.path.join(HERE, "include"), "-I" + os.path.join(libbuild.ROOT, "include"),
+           os.path.join(HERE, "src", "cuda_solver_interface.cpp"), os.path.join(HERE, "src", "modules.cpp"),
+           os.path.join(HERE, "test", "test_packing.cpp"), "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-o", exe]
+    subprocess.check_call(cmd)
+    return exe

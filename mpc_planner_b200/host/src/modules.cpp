@@ -288,8 +288,14 @@ void DecompConstraints::update(State &state, const RealTimeData &, ModuleData &m
     _dummy_b = state.get("x") + 100.;
     for (int k = 0; k < _solver->N - 1 && k < (int)module_data.decomp_polyhedra.size(); k++) {  // polyhedron k -> stage k + 1 (:90-114)
         const auto &poly = module_data.decomp_polyhedra[k];
+        int n_valid = 0;  // rows up to the first zero / NaN normal are used (:97-100), dummies after it
+        while (n_valid < (int)poly.size() && n_valid < _max_constraints) {
+            const double a0 = poly[n_valid].A[0], a1 = poly[n_valid].A[1];
+            if (std::sqrt(a0 * a0 + a1 * a1) < 1e-3 || a0 != a0) break;
+            n_valid++;
+        }
         for (int i = 0; i < _max_constraints; i++) {
-            const bool have = i < (int)poly.size();
+            const bool have = i < n_valid;
             _a1[k + 1][i] = have ? poly[i].A[0] : _dummy_a1;
             _a2[k + 1][i] = have ? poly[i].A[1] : _dummy_a2;
             _b[k + 1][i] = have ? poly[i].b : _dummy_b;

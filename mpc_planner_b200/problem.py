@@ -376,4 +376,5 @@ CONFIGS = {
     "cfg2": config_tmpc,
     "cfg3": config_tmpc_decomp,
     "cfg4": config_safe_horizon,
+    "cfg2_gaussian": lambda: config_tmpc(gaussian=True),  # T-MPC with the CC-MPC submodule (generate_jackal_solver.py:53-73)
 }

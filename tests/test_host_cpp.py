@@ -372,3 +372,13 @@ def test_batched_scenario_solvers_match_python_binding(scenario_exe, tmp_path):
         assert cexit == 1 and np.array_equal(main_x, xt[expect].ravel())
     assert len(ok) >= 1
     solver.close()
+
+
+@pytest.mark.parametrize("name", ["cfg2_gaussian", "cfg3"])
+def test_gaussian_and_decomp_packing_follow_the_reference_cpu(name):
+    """gaussian_constraints.cpp:31-79 (prediction step k-1, static obstacles without uncertainty, k = 0 dummies) and
+    decomp_constraints.cpp:86-114,150-189 (polyhedron k -> stage k+1, rows end at a zero / NaN normal, dummies after)."""
+    exe = build_host.build_packing_test(name)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
