@@ -23,10 +23,15 @@
 #define MPC_PHASE_END \
     }                 \
     __syncthreads();
+// phase end that also ORs a per-thread flag over the CTA (the emulation's flag is one variable shared by the tid loop)
+#define MPC_PHASE_END_OR(flag) \
+    }                          \
+    flag = __syncthreads_or(flag);
 #else
 #define MPC_DEV inline
 #define MPC_PHASE for (int tid = 0; tid < MPC_NT; ++tid) {
 #define MPC_PHASE_END }
+#define MPC_PHASE_END_OR(flag) }
 #endif
 
 // Development aid (-DMPC_PROFILE, scripts/profile_phases.py): thread 0 accumulates clock64() per phase
@@ -95,6 +100,7 @@ MPC_HD void upd_max(double &acc, double v) {
 // (tests/emu: every read advances it by emu_clock_step_ns) so that the CPU suite can pin the iteration-count logic.
 #if !defined(__CUDACC__)
 extern long long g_emu_clock_ns, g_emu_clock_step_ns;
+extern long g_mirror_general;  // stage blocks that went through the CTA-parallel Jacobi (MPC_EMU_TRACE builds)
 #endif
 MPC_DEV long long mpc_clock_ns() {
 #if defined(__CUDA_ARCH__)
@@ -380,14 +386,149 @@ MPC_HD void mirror_stage(const Layout &L, double *st, int part) {
     const int ib[4] = {CFG::IX, CFG::IY, CFG::IS, CFG::HAS_SLACK ? CFG::ISLACK : 0};
     double *Hp = st + S::H;
     if (BLOCKS) {
-        if (st[S::DZN] != 0.0) {  // written by assemble_stage: exactly block diagonal
+        if (st[S::DZN] == 1.0) {  // written by assemble_stage: exactly block diagonal (part 0 may set 2 concurrently)
             if (part == 0) mirror_subblock<NA>(Hp, L.reg_epsilon, ia);
             else mirror_subblock<NB>(Hp, L.reg_epsilon, ib);
             return;
         }
     }
-    if (part == 0) mirror_block<NZ, 0>(Hp, L.reg_epsilon, st + S::T, st + S::WK, ia, ib);
+    // general path: PD test here (MIRROR leaves a block with all eigenvalues above eps unchanged); an indefinite block is
+    // flagged (DZN = 2) for the CTA-parallel Jacobi of mirror_general_cta
+    if (part == 0 && !packed_block_is_pd<NZ>(Hp, L.reg_epsilon)) st[S::DZN] = 2.0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// MIRROR of the stage blocks that are neither block diagonal nor positive definite (CA objective, offset discs):
+// cyclic Jacobi parallelised the classical way -- a round-robin tournament orders the n(n-1)/2 index pairs into m - 1
+// rounds (m = n rounded up to even) of m/2 DISJOINT pairs; thread (stage, j) applies pair j of the round.  Disjoint pairs
+// commute: all column updates (A <- A J, V <- V J) of a round, barrier, all row updates (A <- J' A), barrier.  The three
+// entries a rotation is computed from are only ever changed by that pair itself, so no barrier is needed before them.
+// Serial (one thread per stage, 28 rotations per sweep of an 8 x 8 block) this was 32 % of a cfg 3 solve.
+//   work space per stage: Mw = st[T..] (NZ x NZ, dead between QPs), Vw = st[WK..] (NZ x NZ), (c, s) of the round behind Vw.
+// ---------------------------------------------------------------------------------------------
+MPC_HD void tournament_pair(int m, int r, int j, int &p, int &q) {
+    if (j == 0) {
+        p = r;
+        q = m - 1;
+    } else {
+        const int a = (r + j) % (m - 1), b = (r - j + (m - 1)) % (m - 1);
+        p = a < b ? a : b;
+        q = a < b ? b : a;
+    }
+}
+
+template <class CFG>
+MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
+    typedef SL<CFG> S;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NT = MPC_NT;
+    constexpr int M = (NZ + 1) & ~1, G = M / 2;  // rounds use M indices (index NZ is a dummy when NZ is odd); G pairs per round
+    constexpr int CS = S::WK + NZ * NZ;          // (c, s) of the current round: 2 G doubles
+    static_assert(N * G <= NT, "one thread per (stage, pair of the round)");
+    static_assert(3 * S::NROW >= NZ * NZ && S::DZN - S::WK >= NZ * NZ + 2 * G, "MIRROR work space");
+    const double eps = L.reg_epsilon;
+    // copy the packed block into the work space, V = I (rows split over the G threads of a stage)
+    MPC_PHASE
+    if (tid < N * G) {
+        double *st = sm + (tid / G) * S::STRIDE;
+#if !defined(__CUDACC__) && defined(MPC_EMU_TRACE)
+        if (st[S::DZN] == 2.0 && tid % G == 0) g_mirror_general++;
+#endif
+        if (st[S::DZN] == 2.0)
+            for (int i = tid % G; i < NZ; i += G)
+                for (int j = 0; j < NZ; j++) {
+                    st[S::T + i * NZ + j] = st[S::H + trisym(i, j)];
+                    st[S::WK + i * NZ + j] = (i == j) ? 1.0 : 0.0;
+                }
+    }
+    MPC_PHASE_END
+    for (int sweep = 0; sweep < 30; sweep++) {
+        int active = 0;
+        MPC_PHASE
+        if (tid < N * G && tid % G == 0) {  // convergence of each flagged stage (same rule as the register Jacobi)
+            double *st = sm + (tid / G) * S::STRIDE;
+            if (st[S::DZN] == 2.0) {
+                const double *Mw = st + S::T;
+                double offd = 0.0, diag = 0.0;
+                for (int i = 0; i < NZ; i++) {
+                    diag += Mw[i * NZ + i] * Mw[i * NZ + i];
+                    for (int j = i + 1; j < NZ; j++) offd += Mw[i * NZ + j] * Mw[i * NZ + j];
+                }
+                if (offd <= 1e-30 * (diag + offd) || offd == 0.0) st[S::DZN] = 3.0;  // converged: rebuild below
+                else active |= 1;
+            }
+        }
+        MPC_PHASE_END_OR(active)
+        if (!active) break;
+        for (int r = 0; r < M - 1; r++) {
+            MPC_PHASE
+            if (tid < N * G) {  // rotation of the own pair; column updates of A and V
+                double *st = sm + (tid / G) * S::STRIDE;
+                const int j = tid % G;
+                int p, q;
+                tournament_pair(M, r, j, p, q);
+                double c = 1.0, sn = 0.0;
+                if (st[S::DZN] == 2.0 && q < NZ) {
+                    double *Mw = st + S::T, *Vw = st + S::WK;
+                    const double apq = Mw[p * NZ + q], app = Mw[p * NZ + p], aqq = Mw[q * NZ + q];
+                    if (!(fabs(apq) <= 1e-19 * (fabs(app) + fabs(aqq)))) {  // rotations that cannot change the diagonal are skipped
+                        jacobi_rotation(app, aqq, apq, c, sn);
+                        for (int k = 0; k < NZ; k++) {
+                            const double mkp = Mw[k * NZ + p], mkq = Mw[k * NZ + q];
+                            Mw[k * NZ + p] = c * mkp - sn * mkq;
+                            Mw[k * NZ + q] = sn * mkp + c * mkq;
+                            const double vkp = Vw[k * NZ + p], vkq = Vw[k * NZ + q];
+                            Vw[k * NZ + p] = c * vkp - sn * vkq;
+                            Vw[k * NZ + q] = sn * vkp + c * vkq;
+                        }
+                    }
+                }
+                st[CS + 2 * j] = c;
+                st[CS + 2 * j + 1] = sn;
+            }
+            MPC_PHASE_END
+            MPC_PHASE
+            if (tid < N * G) {  // row updates
+                double *st = sm + (tid / G) * S::STRIDE;
+                const int j = tid % G;
+                int p, q;
+                tournament_pair(M, r, j, p, q);
+                const double c = st[CS + 2 * j], sn = st[CS + 2 * j + 1];
+                if (st[S::DZN] == 2.0 && q < NZ && sn != 0.0) {
+                    double *Mw = st + S::T;
+                    for (int k = 0; k < NZ; k++) {
+                        const double mpk = Mw[p * NZ + k], mqk = Mw[q * NZ + k];
+                        Mw[p * NZ + k] = c * mpk - sn * mqk;
+                        Mw[q * NZ + k] = sn * mpk + c * mqk;
+                    }
+                }
+            }
+            MPC_PHASE_END
+        }
+    }
+    // rebuild V f(D) V' into the packed block (rows split over the G threads): eigenvalues e -> eps if |e| <= eps, else |e|
+    MPC_PHASE
+    if (tid < N * G) {
+        double *st = sm + (tid / G) * S::STRIDE;
+        if (st[S::DZN] >= 2.0) {
+            const double *Mw = st + S::T, *Vw = st + S::WK;
+            double e[NZ];
+            for (int k = 0; k < NZ; k++) {
+                double l = Mw[k * NZ + k];
+                if (l >= -eps && l <= eps) l = eps;
+                else if (l < 0.0) l = -l;
+                e[k] = l;
+            }
+            for (int i = tid % G; i < NZ; i += G)
+                for (int j = 0; j <= i; j++) {
+                    double acc = 0.0;
+                    for (int k = 0; k < NZ; k++) acc += Vw[i * NZ + k] * e[k] * Vw[j * NZ + k];
+                    st[S::H + tri(i, j)] = acc;
+                }
+        }
+    }
+    MPC_PHASE_END
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // Riccati sweeps.  The recursion is a serial chain over the horizon whose per-stage blocks are
@@ -1407,13 +1548,18 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
             if ((tid & 31) < (N + NT / 32 - 1) / (NT / 32) && k < N) assemble_stage<CFG>(L, sm + k * S::STRIDE);
         }
         MPC_PHASE_END
+        int need_general = 0;
         MPC_PHASE
         {   // MIRROR: (stage, part) items spread over the warps: the Jacobi sweeps diverge per item
             constexpr int NI = 2 * N, NW = NT / 32;
             const int it = (tid & 31) * NW + (tid >> 5);
-            if ((tid & 31) < (NI + NW - 1) / NW && it < NI) mirror_stage<CFG>(L, sm + (it >> 1) * S::STRIDE, it & 1);
+            if ((tid & 31) < (NI + NW - 1) / NW && it < NI) {
+                mirror_stage<CFG>(L, sm + (it >> 1) * S::STRIDE, it & 1);
+                if (sm[(it >> 1) * S::STRIDE + S::DZN] == 2.0) need_general |= 1;
+            }
         }
-        MPC_PHASE_END
+        MPC_PHASE_END_OR(need_general)
+        if (need_general) mirror_general_cta<CFG>(L, sm);
         MPC_TICK(TK_ASM)
         // feedback: QP
         int iters = 0;

@@ -13,7 +13,8 @@ if "--build" in sys.argv or not os.path.exists(lib_prof):
         sys.exit(0)
 binding.LIB_PATH = lib_prof
 P = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 8
-spec = pb.config_tmpc()
+cfg = next((a for a in sys.argv[1:] if a in pb.CONFIGS), "cfg2")
+spec = pb.CONFIGS[cfg]()
 base = scenes.make_scene_batch(spec, max(1, min(P // 8, 32)), 8, seed=1)
 reps = (P + len(base["xinit"]) - 1) // len(base["xinit"])
 xi, x0, par = (np.tile(base[k], (reps, 1))[:P] for k in ("xinit", "x0", "params"))
@@ -23,6 +24,6 @@ xt, ut, info, best = s.solve(xi, x0, par)
 names = ["lin", "assemble(mirror)", "ipm_init", "PA", "PB rows", "acc0", "reduce", "factor", "solve", "PD rows", "acc1", "PF rows", "sqp step", "final"]
 prof = ut.reshape(P, -1)[:, :16]
 tot = prof[:, :14].sum(axis=1)
-print(f"P={P}: mean total cycles {tot.mean():.0f}; mean qp_iter {np.mean([i['qp_iter'] for i in info]):.1f}")
+print(f"{cfg} P={P}: mean total cycles {tot.mean():.0f}; mean qp_iter {np.mean([i['qp_iter'] for i in info]):.1f}")
 for i, n in enumerate(names):
     print(f"  {n:18s} {prof[:, i].mean():12.0f} cycles  {100 * prof[:, i].mean() / tot.mean():5.1f}%")

@@ -10,12 +10,13 @@
 namespace mpcgpu { extern long g_mirror_slow, g_mirror_calls; }
 #include "../../mpc_planner_b200/csrc/registry.cuh"
 
-namespace mpcgpu { long g_mirror_slow = 0, g_mirror_calls = 0; long long g_emu_clock_ns = 0, g_emu_clock_step_ns = 0; }
+namespace mpcgpu { long g_mirror_slow = 0, g_mirror_calls = 0, g_mirror_general = 0; long long g_emu_clock_ns = 0, g_emu_clock_step_ns = 0; }
 using namespace mpcgpu;
 static double g_emu_timeout_s = 0.0;
 // fake clock of the emulation: every clock read advances by `step_ns`; `timeout_s` as mpcgpu_set_timeout
 extern "C" void emu_set_timeout(double timeout_s, long long step_ns) { g_emu_timeout_s = timeout_s; g_emu_clock_step_ns = step_ns; g_emu_clock_ns = 0; }
 extern "C" void emu_mirror_stats(long *calls, long *slow) { *calls = g_mirror_calls; *slow = g_mirror_slow; }
+extern "C" long emu_mirror_general_count() { return g_mirror_general; }
 
 template <class CFG>
 static int solve_cfg(const mpcgpu_problem_desc &d, int P, const double *xinit, const double *x0, const double *params,

@@ -73,6 +73,28 @@ def test_lane_cooperative_factorisation_variant_matches_oracle(tmp_path):
         assert n_ok >= 1
 
 
+def test_general_mirror_path_runs_the_parallel_jacobi(tmp_path):
+    """cfg 3 (CA objective: stage Hessians are not block diagonal) must reach mirror_general_cta -- the round-robin parallel
+    cyclic Jacobi -- and still match the oracle's eigen-decomposition based MIRROR."""
+    import ctypes
+
+    lib = emu.build_variant(["MPC_EMU_TRACE"], str(tmp_path / "libmpcgpu_emu_trace.so"))
+    spec = SPECS["cfg3"]
+    b = scenes.make_scene_batch(spec, 1, 4, seed=31)
+    xt, ut, info = oracle.solve_batch(spec, b["xinit"], b["x0"], b["params"])
+    ext, eut, einfo = emu.solve_batch(spec, b["xinit"], b["x0"], b["params"], library=lib)
+    L = ctypes.CDLL(lib)
+    L.emu_mirror_general_count.restype = ctypes.c_long
+    assert L.emu_mirror_general_count() > 0
+    n_ok = 0
+    for i in range(4):
+        assert einfo[i]["exit_code"] == info[i]["exit_code"]
+        if info[i]["exit_code"] == 1:
+            n_ok += 1
+            np.testing.assert_allclose(ext[i], xt[i], rtol=1e-6, atol=1e-6)
+    assert n_ok >= 1
+
+
 def test_solver_timeout_iteration_count_logic():
     """Solver::solve()'s timeout (acados_solver_interface.cpp:91-117) as restated in csrc/sqp_core.cuh: stop after iteration
     i once elapsed + average iteration time >= budget.  The emulation's clock advances 1 ms per read, so: start = 1 ms,
