@@ -17,6 +17,8 @@ static double g_emu_timeout_s = 0.0;
 extern "C" void emu_set_timeout(double timeout_s, long long step_ns) { g_emu_timeout_s = timeout_s; g_emu_clock_step_ns = step_ns; g_emu_clock_ns = 0; }
 extern "C" void emu_mirror_stats(long *calls, long *slow) { *calls = g_mirror_calls; *slow = g_mirror_slow; }
 extern "C" long emu_mirror_general_count() { return g_mirror_general; }
+// round-robin schedule of the parallel Jacobi (csrc/sqp_core.cuh tournament_pair): pair j of round r for m indices
+extern "C" void emu_tournament_pair(int m, int r, int j, int *p, int *q) { tournament_pair(m, r, j, *p, *q); }
 
 template <class CFG>
 static int solve_cfg(const mpcgpu_problem_desc &d, int P, const double *xinit, const double *x0, const double *params,

@@ -73,6 +73,26 @@ def test_lane_cooperative_factorisation_variant_matches_oracle(tmp_path):
         assert n_ok >= 1
 
 
+@pytest.mark.parametrize("m", [2, 4, 6, 8, 10])
+def test_tournament_schedule_covers_every_pair_once_with_disjoint_rounds(m):
+    """The parallel cyclic Jacobi relies on it: m - 1 rounds of m/2 pairwise DISJOINT index pairs, every pair exactly once."""
+    import ctypes
+
+    L = emu.lib()
+    seen = set()
+    for r in range(m - 1):
+        used = set()
+        for j in range(m // 2):
+            p, q = ctypes.c_int(), ctypes.c_int()
+            L.emu_tournament_pair(m, r, j, ctypes.byref(p), ctypes.byref(q))
+            assert 0 <= p.value < q.value < m
+            assert p.value not in used and q.value not in used  # disjoint within the round
+            used |= {p.value, q.value}
+            assert (p.value, q.value) not in seen
+            seen.add((p.value, q.value))
+    assert len(seen) == m * (m - 1) // 2
+
+
 def test_general_mirror_path_runs_the_parallel_jacobi(tmp_path):
     """cfg 3 (CA objective: stage Hessians are not block diagonal) must reach mirror_general_cta -- the round-robin parallel
     cyclic Jacobi -- and still match the oracle's eigen-decomposition based MIRROR."""
