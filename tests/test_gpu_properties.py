@@ -186,3 +186,62 @@ def test_solver_timeout_bounds_the_rti_iterations(binding):
     xt, ut, info, _ = solver.solve(b["xinit"], b["x0"], b["params"])
     assert np.array_equal(xt, xt10) and [i["sqp_iter"] for i in info] == [i["sqp_iter"] for i in info10]
     solver.close()
+
+
+def _rk4_family(spec, x, u):
+    """ERK4 x 3 of the unicycle family (states x, y, psi, v, spline[, slack]; slack' = 0), vectorised over solves."""
+    out = _rk4(x[:, :5], u, spec.dt)
+    return np.concatenate([out, x[:, 5:]], axis=1) if x.shape[1] > 5 else out
+
+
+def check_batch_properties(spec, b, xt, ut, info, best, group):
+    """Size-independent properties of one solved batch (shared by the GPU test below and its CPU dry run on the emulation)."""
+    P = len(info)
+    codes = np.array([i["exit_code"] for i in info])
+    ok = codes == 1
+    assert ok.mean() > 0.5 and set(np.unique(codes)) <= {0, 1, 2, 3, 4}
+    np.testing.assert_allclose(xt[ok, 0], b["xinit"][ok], atol=1e-12)
+    worst = max(np.abs(_rk4_family(spec, xt[ok, k], ut[ok, k]) - xt[ok, k + 1]).max() for k in range(spec.N))
+    assert worst < 1e-2 and max(i["res_eq"] for i, o in zip(info, ok) if o) <= 1e-2
+    d = spec.desc()
+    lo, up = np.array(list(d.lower_bound)[: spec.nz]), np.array(list(d.upper_bound)[: spec.nz])
+    assert (ut[ok] >= lo[: spec.nu] - 1e-3).all() and (ut[ok] <= up[: spec.nu] + 1e-3).all()
+    assert (xt[ok, 1:spec.N] >= lo[spec.nu:] - 1e-3).all() and (xt[ok, 1:spec.N] <= up[spec.nu:] + 1e-3).all()
+    obj = np.array([i["pobj"] for i in info]).reshape(-1, group)
+    okg = ok.reshape(-1, group)
+    for g in range(P // group):
+        if okg[g].any():
+            want = int(np.argmin(np.where(okg[g], obj[g], np.inf)))
+            assert best[g] == want or obj[g, best[g]] == obj[g, want]
+        else:
+            assert best[g] == -1
+
+
+@pytest.mark.parametrize("name,S,G", [("cfg3", 1, 64), ("cfg4", 256, 4)])
+def test_baseline_size_batches_of_the_other_configs(binding, name, S, G):
+    """BASELINE configs[2] (T-MPC++ P = 64, N = 30, decomp halfspaces, CA cost) and configs[3] (SH-MPC: 256 scenario sets x 4
+    guesses) at their full batch sizes: size-independent properties, a sample against the oracle, determinism."""
+    from oracle import oracle
+
+    spec = pb.CONFIGS[name]()
+    base = scenes.make_scene_batch(spec, min(S, 16), G, seed=21)  # the batches scripts/config_sweep.py measures
+    reps = S // min(S, 16)
+    b = {k: np.tile(base[k], (reps, 1)) for k in ("xinit", "x0", "params")}
+    P = S * G
+    solver = binding.BatchSolver(spec, P)
+    solver.set_group(G)
+    xt, ut, info, best = solver.solve(b["xinit"], b["x0"], b["params"])
+    check_batch_properties(spec, b, xt, ut, info, best, G)
+    n = 6
+    oxt, out, oinfo = oracle.solve_batch(spec, b["xinit"][:n], b["x0"][:n], b["params"][:n])
+    for i in range(n):
+        assert info[i]["exit_code"] == oinfo[i]["exit_code"] and info[i]["qp_status"] == oinfo[i]["qp_status"]
+        if oinfo[i]["exit_code"] == 1:
+            np.testing.assert_allclose(xt[i], oxt[i], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(ut[i], out[i], rtol=1e-6, atol=1e-6)
+    xt2, ut2, info2, best2 = solver.solve(b["xinit"], b["x0"], b["params"])
+    np.testing.assert_array_equal(xt, xt2)
+    np.testing.assert_array_equal(best, best2)
+    if reps > 1:  # the batch is tiled: replicas must agree bit for bit
+        np.testing.assert_array_equal(xt[: P // reps], xt[P // reps: 2 * (P // reps)])
+    solver.close()
