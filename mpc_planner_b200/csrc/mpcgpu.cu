@@ -1,7 +1,7 @@
 // mpcgpu.cu -- CUDA kernels and the C ABI (include/mpcgpu.h) of the B200 batched SQP backend.
 //
 // Launch geometry: one 128-thread CTA per solve, the whole NLP/QP of that solve in shared memory
-// (SL<CFG>::TOTAL doubles, ~70 KB for the T-MPC stack => 3 CTAs = 12 warps per SM).
+// (SL<CFG>::TOTAL doubles: 56 KB for the T-MPC stack => 4 CTAs = 16 warps per SM).
 // Kernels per batch:  transpose_params (reference stage-major parameters -> lane-major so that
 // lane = stage loads coalesce)  ->  sqp_kernel  ->  select_best (FindBestPlanner argmin).
 #include <cuda_runtime.h>

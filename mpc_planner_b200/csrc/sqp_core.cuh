@@ -4,13 +4,14 @@
 // Replaces, for the hot path, what the reference delegates to acados (SQP-RTI), HPIPM (IPM QP) and
 // BLASFEO: per RTI iteration  linearise all stages (threads = stage x function part)  ->
 // MIRROR-regularise  ->  Mehrotra predictor-corrector interior point on the stage-structured QP
-// (threads = stage x inequality row) with a Riccati factorisation (threads = matrix entries x
-// split-K)  ->  full step.
+// (threads = stage x inequality row) with a Riccati factorisation (one thread, register resident;
+// DESIGN.md 4 lists the cooperative variants that were measured)  ->  full step.
 //
 // Structure: the routine is a sequence of CTA "phases".  Inside a phase every thread works on data
 // written by earlier phases and writes a disjoint part of shared memory; phases are separated by
-// __syncthreads().  No register state crosses a phase boundary, so the same source compiles for
-// the host as a sequential NT-thread emulation (tests/emu), used to debug without a GPU.
+// __syncthreads().  No register state crosses a phase boundary (exceptions: thread 0's timeout clocks and CTA-uniform
+// scalars), so the same source compiles for the host as a sequential NT-thread emulation (tests/emu), used to debug
+// without a GPU.
 #pragma once
 
 #include "stage_functions.cuh"
