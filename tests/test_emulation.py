@@ -9,6 +9,7 @@ from mpc_planner_b200 import problem as pb
 from mpc_planner_b200 import scenes
 from oracle import oracle
 from tests.emu import emu
+from tests.util import same_status
 
 SPECS = {
     "cfg1": pb.config_basic(),
@@ -44,8 +45,7 @@ def test_emulated_kernel_solves_match_oracle(name, S, P):
     ext, eut, einfo = emu.solve_batch(spec, b["xinit"], b["x0"], b["params"])
     n_ok = 0
     for i in range(S * P):
-        assert einfo[i]["exit_code"] == info[i]["exit_code"], (i, einfo[i], info[i])
-        assert einfo[i]["qp_status"] == info[i]["qp_status"]
+        assert same_status(einfo[i], info[i]), (i, einfo[i], info[i])
         if info[i]["exit_code"] == 1:
             n_ok += 1
             np.testing.assert_allclose(ext[i], xt[i], rtol=1e-6, atol=1e-6)
@@ -65,7 +65,7 @@ def test_lane_cooperative_factorisation_variant_matches_oracle(tmp_path):
         ext, eut, einfo = emu.solve_batch(spec, b["xinit"], b["x0"], b["params"], library=lib)
         n_ok = 0
         for i in range(S * P):
-            assert einfo[i]["exit_code"] == info[i]["exit_code"] and einfo[i]["qp_status"] == info[i]["qp_status"]
+            assert same_status(einfo[i], info[i])
             if info[i]["exit_code"] == 1:
                 n_ok += 1
                 np.testing.assert_allclose(ext[i], xt[i], rtol=1e-6, atol=1e-6)

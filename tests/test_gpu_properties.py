@@ -6,6 +6,7 @@ import pytest
 
 from mpc_planner_b200 import problem as pb
 from mpc_planner_b200 import scenes
+from tests.util import same_status
 
 pytestmark = pytest.mark.gpu
 
@@ -176,7 +177,7 @@ def test_solver_timeout_bounds_the_rti_iterations(binding):
     spec1 = dataclasses.replace(spec, n_sqp=1)
     oxt, out, oinfo = oracle.solve_batch(spec1, b["xinit"], b["x0"], b["params"])
     for i in range(32):
-        assert info1[i]["exit_code"] == oinfo[i]["exit_code"] and info1[i]["qp_status"] == oinfo[i]["qp_status"]
+        assert same_status(info1[i], oinfo[i])
     np.testing.assert_allclose(xt1, oxt, rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(ut1, out, rtol=1e-6, atol=1e-6)
     solver.set_timeout(10.0)
@@ -235,7 +236,7 @@ def test_baseline_size_batches_of_the_other_configs(binding, name, S, G):
     n = 6
     oxt, out, oinfo = oracle.solve_batch(spec, b["xinit"][:n], b["x0"][:n], b["params"][:n])
     for i in range(n):
-        assert info[i]["exit_code"] == oinfo[i]["exit_code"] and info[i]["qp_status"] == oinfo[i]["qp_status"]
+        assert same_status(info[i], oinfo[i])
         if oinfo[i]["exit_code"] == 1:
             np.testing.assert_allclose(xt[i], oxt[i], rtol=1e-6, atol=1e-6)
             np.testing.assert_allclose(ut[i], out[i], rtol=1e-6, atol=1e-6)
