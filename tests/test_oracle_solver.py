@@ -284,3 +284,33 @@ def test_later_rti_steps_solve_the_exact_hessian_qp_an_independent_solver_finds(
         checked += 1
     assert checked >= 1
     print("stage blocks with an eigenvalue below -eps (MIRROR active):", indefinite)
+
+
+def test_an_independent_nlp_solver_reaches_the_same_optimum_from_the_same_warm_start():
+    """NLP level, no shared starting information: scipy's SLSQP (quasi-Newton SQP on the dense NLP, no MIRROR, no IPM, no
+    Riccati) is started from the WARM START -- not from the oracle's solution -- and must end at the oracle's converged point
+    whenever both land in the same basin (the NLP is non-convex: obstacles can be passed on either side; where the two end
+    in different basins nothing can be compared and the oracle's basin must then simply be feasible)."""
+    from scipy.optimize import minimize
+
+    spec = pb.config_tmpc()
+    spec.n_sqp = 40  # the oracle's algorithm run to convergence (10 RTI steps stop ~1e-4 short, see above)
+    b = scenes.make_scene_batch(spec, 2, 3, seed=11)
+    xt, ut, info = oracle.solve_batch(spec, b["xinit"], b["x0"], b["params"])
+    N, nu, nz = spec.N, spec.nu, spec.nz
+    same_basin = 0
+    for i in (0, 3, 4):
+        assert info[i]["exit_code"] == 1
+        nvar, cost, cost_grad, eq, ineq = _nlp_pieces(spec, b["xinit"][i], b["params"][i])
+        z0 = b["x0"][i].reshape(N + 1, nz)
+        w_start = np.concatenate([z0[:N].ravel(), z0[N, nu:]])
+        w_or = np.concatenate([np.concatenate([ut[i], xt[i, :N]], axis=1).ravel(), xt[i, N]])
+        res = minimize(cost, w_start, jac=cost_grad, method="SLSQP", constraints=[dict(type="eq", fun=eq), dict(type="ineq", fun=ineq)],
+                       options=dict(maxiter=300, ftol=1e-12))
+        assert res.success, res.message
+        assert np.abs(eq(w_or)).max() < 1e-6 and ineq(w_or).min() > -1e-6
+        if np.abs(res.x - w_or).max() < 5e-2:  # same basin
+            same_basin += 1
+            assert np.abs(res.x - w_or).max() < 2e-3
+            assert res.fun == pytest.approx(info[i]["pobj"], abs=5e-5)  # complementarity <= qp_tol per active row
+    assert same_basin >= 2
