@@ -959,6 +959,284 @@ MPC_DEV void riccati_factor_lanes(double *sm) {
     MPC_PHASE_END
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward factorisation on the FP64 tensor-core path (DMMA.8x8x4): one warp, all 32 lanes.
+//
+// The single-thread sweep above issues ~300 FP64 + ~210 other instructions per stage with 1 of 32 lanes useful and
+// needs ~1150 cycles per stage (1750 with four solves per SM).  Here the three matrix products of a stage are five
+// `mma.sync.m8n8k4.f64` (measured on B200: 26 cycles dependent, 18 cycles issue-to-issue; scripts/micro/dmma_micro.cu):
+//   index n in [0, NZ]: row of the augmented block (n < NZ: variable of z = [u; x]; n = NZ: the "vector row" that carries
+//   the affine recursion, which has the algebra of one more row);  a, r, k in [0, NZ): variables of z.
+//     Pt[n][a]   cost-to-go of the next stage:  x rows / columns = P+,  vector row = pv+;   u rows / columns: unused
+//     GEMM 1     Wt[n][r] = sum_k At[n][k] Pt[r][k]      At[n][k] = [B A]_{k,n} (x rows k),  At[NZ][k] = c_k
+//                         = (P+ [B A | c])'              the vector row then receives + pv+  (q = pv+ + P+ c)
+//     GEMM 2     Mt[n][a] = sum_r Wt[n][r] [B A]_{r,a} + (H + G | gt)[n][a]         = M (symmetric) | m
+//     Cholesky   of M_uu in closed form (as in the serial sweep), L[n][0..1] = rows of L_xu (x rows) | y (vector row)
+//     GEMM 3     Pt[n][a] = Mt[n][a] - sum_{k<2} L[n][k] L[a][k]                    = P | pv
+// Fragment layouts of m8n8k4 (g = lane / 4, q = lane % 4):  A: (row g, k q);  B: (k q, column g);  C/D: (row g,
+// columns 2q, 2q + 1).  A product's contraction index may be enumerated in any order, so the two C registers of a lane
+// serve directly as the A fragments (and, Pt being symmetric in its x block, as the B fragments) of the next product
+// with the contraction split into "even" (k = 2q) and "odd" (k = 2q + 1) halves: NO shuffle or shared-memory round trip
+// between the products.  Per stage the chain is 2 + 2 + 1 dependent DMMA, one broadcast of M_uu, the two reciprocal
+// square roots and two quad-local shuffles: ~330 cycles.  Everything else of a stage (its [B A], c, H + G, gt) is
+// loop-carried-independent shared-memory traffic.  NZ <= 8 (one column tile); the vector row makes a second row tile
+// for the slack models (NZ = 8).  Rows / columns of Pt that belong to u hold finite don't-care values: every product
+// that contracts over them multiplies by structural zeros of [B A].
+// Device only: the host emulation (tests/emu) runs the single-thread sweep, to which this one is algebraically identical.
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+// Two independent reciprocal square roots of normal positive numbers, their instruction streams interleaved.  Arithmetic of
+// CUDA's rsqrt(double) fast path: MUFU.RSQ64H seed y (upper word), e = 1 - x y^2, r = y + (y e)(1/2 + 3/8 e) -- bitwise the
+// same result for normal arguments; zero / negative / non-finite arguments (an indefinite input block: the QP has failed)
+// give NaN where rsqrt() may give inf, and every caller multiplies the result by finite terms that turn inf into NaN too.
+MPC_DEV void mpc_rsqrt_pair(const double x0, const double x1, double &r0, double &r1) {
+    double y0, y1;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x0));
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y1) : "d"(x1));
+    const double e0 = fma(x0, -(y0 * y0), 1.0), e1 = fma(x1, -(y1 * y1), 1.0);
+    const double p0 = fma(e0, 0.375, 0.5), p1 = fma(e1, 0.375, 0.5);
+    const double t0 = y0 * e0, t1 = y1 * e1;
+    r0 = fma(p0, t0, y0);
+    r1 = fma(p1, t1, y1);
+}
+
+MPC_DEV void mpc_dmma(double &d0, double &d1, const double a, const double b, const double c0, const double c1) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(d0), "=d"(d1)
+        : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+// shared-memory accesses of the tensor-core sweep by 32-bit shared-window address: the window base of the CTA is read
+// once (the compiler otherwise re-derives it from SR_CgaCtaId inside the stage loop when registers are tight)
+MPC_DEV double mpc_lds(unsigned addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+MPC_DEV double mpc_lds_if(bool p, unsigned addr) {  // p ? load : 0.0  (one predicated LDS)
+    double v = 0.0;
+    asm("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q ld.shared.f64 %0, [%1];\n}" : "+d"(v) : "r"(addr), "r"((int)p));
+    return v;
+}
+MPC_DEV void mpc_sts_if(bool p, unsigned addr, double v) {
+    asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}" ::"r"(addr), "d"(v), "r"((int)p) : "memory");
+}
+
+template <class CFG>
+MPC_DEV void riccati_factor_mma(double *sm) {
+    typedef SL<CFG> S;
+    typedef RicIdx<CFG> R;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
+    constexpr int RT = (NZ + 1 + 7) / 8;              // row tiles: NZ variables + the vector row
+    constexpr int VT = NZ / 8, VG = NZ % 8;           // tile / row group of the vector row
+    static_assert(NU == 2 && NZ <= 8, "one column tile; input block factorised in closed form for nu = 2");
+    const int serial_tid = (int)sm[S::W_BASE + S::W_STID];
+    if (((int)threadIdx.x & ~31) == serial_tid) {
+        const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+        const unsigned FULL = 0xffffffffu;
+        unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+        asm volatile("" : "+r"(sbase));
+        // ---- per-lane tables (loop invariant): byte offsets inside a stage image; absent entries are flagged ----
+        // slot s <-> column / contraction index a_s = 2q + s;  its x row l_s = a_s - NU
+        int f_off[2], c_off[2], h_off[RT][2], gb_off[RT][2], gs_off[RT][2], gd_off[RT][2], p_off[RT][2], lx_off[RT];
+        int flags = 0;          // bit 0/1: f_has[s]; 2/3: c_has[s]
+        int fl[RT][2], fx[RT];  // per (row tile, slot): bits {0: h, 1: gd, 2: gb, 3: gs, 4: p};  per row tile: own L entry is stored
+        double f_id[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int a = 2 * q + s, l = a - NU;
+            const bool lv = (l >= 0 && l < NX);
+            // [B A]_{l, g}: B (g < NU), else A = I + E with E stored for its non-zero columns (psi, v)
+            f_off[s] = 0; f_id[s] = 0.0;
+            if (lv && g < NZ) {
+                if (g < NU) { flags |= 1 << s; f_off[s] = S::BB + l * NU + g; }
+                else {
+                    const int j = g - NU, e = (j == 2) ? 0 : ((j == 3) ? 1 : -1);
+                    f_id[s] = (l == j) ? 1.0 : 0.0;
+                    if (e >= 0) { flags |= 1 << s; f_off[s] = S::BE + l * NE + e; }
+                }
+            }
+            if (lv) flags |= 4 << s;
+            c_off[s] = S::C + (lv ? l : 0);
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {
+                const int n = 8 * rt + g;
+                int &F = fl[rt][s];
+                F = 0;
+                h_off[rt][s] = gb_off[rt][s] = gs_off[rt][s] = gd_off[rt][s] = p_off[rt][s] = 0;
+                if (a < NZ) {
+                    if (n < NZ) {
+                        F |= 1; h_off[rt][s] = S::H + trisym(n, a);
+                        if (n == a) { F |= 2; gd_off[rt][s] = S::GD + a; }
+                        const int an = (n == CFG::IX) ? 0 : (n == CFG::IY) ? 1 : (n == CFG::IPSI) ? 2 : -1;
+                        const int aa = (a == CFG::IX) ? 0 : (a == CFG::IY) ? 1 : (a == CFG::IPSI) ? 2 : -1;
+                        if (an >= 0 && aa >= 0) { F |= 4; gb_off[rt][s] = S::GB + trisym(an, aa); }
+                        if (CFG::ANY_SLACK_ROWS) {
+                            if (n == CFG::ISLACK && aa >= 0) { F |= 8; gs_off[rt][s] = S::GS + aa; }
+                            if (a == CFG::ISLACK && an >= 0) { F |= 8; gs_off[rt][s] = S::GS + an; }
+                            if (n == CFG::ISLACK && a == CFG::ISLACK) { F |= 8; gs_off[rt][s] = S::GS + 3; }
+                        }
+                        if (n >= NU && l >= 0 && l <= n - NU) { F |= 16; p_off[rt][s] = S::P + tri(n - NU, l); }  // lower triangle of P
+                    } else if (n == NZ) {
+                        F |= 1; h_off[rt][s] = S::GT + a;
+                        if (lv) { F |= 16; p_off[rt][s] = S::PV + l; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int rt = 0; rt < RT; rt++) {
+            const int n = 8 * rt + g;
+            lx_off[rt] = 0;
+            fx[rt] = 0;
+            if (q < NU) {
+                if (n >= NU && n < NZ) { fx[rt] = 1; lx_off[rt] = S::LXU + (n - NU) * NU + q; }
+                if (n == NZ) { fx[rt] = 1; lx_off[rt] = S::YV + q; }
+            }
+        }
+        // keep the tables in registers (opaque to the optimiser: it would otherwise re-derive them from the lane id
+        // through select chains inside the stage loop)
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            f_off[s] *= 8; c_off[s] *= 8;
+            mpc_opaque(f_off[s]); mpc_opaque(c_off[s]);
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {
+                h_off[rt][s] *= 8; gd_off[rt][s] *= 8; gb_off[rt][s] *= 8; gs_off[rt][s] *= 8; p_off[rt][s] *= 8;
+                mpc_opaque(h_off[rt][s]); mpc_opaque(gd_off[rt][s]); mpc_opaque(gb_off[rt][s]); mpc_opaque(p_off[rt][s]);
+                if (CFG::ANY_SLACK_ROWS) mpc_opaque(gs_off[rt][s]);
+                mpc_opaque(fl[rt][s]);
+            }
+        }
+#pragma unroll
+        for (int rt = 0; rt < RT; rt++) { lx_off[rt] *= 8; mpc_opaque(lx_off[rt]); mpc_opaque(fx[rt]); }
+        mpc_opaque(flags);
+        const bool is_vec = (g == VG), lane0 = (lane == 0);
+        // ---- terminal node: P_N (eps I after MIRROR), pv_N = gt_N ----
+        double Pt[RT][2];
+        {
+            const double *stN = sm + N * S::STRIDE;
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++)
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const int n = 8 * rt + g, a = 2 * q + s, l = a - NU;
+                    double v = 0.0;
+                    if (l >= 0 && l < NX) {
+                        if (n >= NU && n < NZ) v = stN[S::P + trisym(n - NU, l)];
+                        if (n == NZ) {
+                            v = stN[S::GT + a];
+                            sm[N * S::STRIDE + S::PV + l] = v;
+                        }
+                    }
+                    Pt[rt][s] = v;
+                }
+        }
+        // stage constants of stage k (independent of the recursion): loaded one stage ahead, all loads issued before
+        // any of them is consumed
+        double fv[2], cv[2], ci[RT][2];
+        double raw[RT][2][4];
+        auto load_stage = [&](const unsigned st) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                fv[s] = mpc_lds_if((flags >> s) & 1, st + f_off[s]);
+                cv[s] = mpc_lds_if((flags >> (2 + s)) & 1, st + c_off[s]);
+#pragma unroll
+                for (int rt = 0; rt < RT; rt++) {
+                    raw[rt][s][0] = mpc_lds_if(fl[rt][s] & 1, st + h_off[rt][s]);
+                    raw[rt][s][1] = mpc_lds_if(fl[rt][s] & 2, st + gd_off[rt][s]);
+                    raw[rt][s][2] = mpc_lds_if(fl[rt][s] & 4, st + gb_off[rt][s]);
+                    raw[rt][s][3] = CFG::ANY_SLACK_ROWS ? mpc_lds_if(fl[rt][s] & 8, st + gs_off[rt][s]) : 0.0;
+                }
+            }
+        };
+        auto finish_stage = [&]() {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                fv[s] += f_id[s];
+#pragma unroll
+                for (int rt = 0; rt < RT; rt++) {
+                    double v = raw[rt][s][0] + raw[rt][s][1];  // same association as the serial sweep: (H + GD) + GB (+ GS)
+                    v += raw[rt][s][2];
+                    if (CFG::ANY_SLACK_ROWS) v += raw[rt][s][3];
+                    ci[rt][s] = v;
+                }
+            }
+        };
+        load_stage(sbase + (N - 1) * S::STRIDE * 8);
+        finish_stage();
+#pragma unroll 1
+        for (int k = N - 1; k >= 0; k--) {
+            const unsigned st = sbase + k * (S::STRIDE * 8), stn = st + S::STRIDE * 8;
+            // GEMM 1: Wt = At Pt' (+ pv+ on the vector row)
+            double w[RT][2];
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {
+                const int n = 8 * rt + g;
+                const double a0 = (n < NZ) ? fv[0] : ((n == NZ) ? cv[0] : 0.0);
+                const double a1 = (n < NZ) ? fv[1] : ((n == NZ) ? cv[1] : 0.0);
+                mpc_dmma(w[rt][0], w[rt][1], a0, Pt[0][0], 0.0, 0.0);
+                mpc_dmma(w[rt][0], w[rt][1], a1, Pt[0][1], w[rt][0], w[rt][1]);
+            }
+            const double fb0 = fv[0], fb1 = fv[1];
+            double cc[RT][2];
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {
+                cc[rt][0] = ci[rt][0];
+                cc[rt][1] = ci[rt][1];
+            }
+            load_stage(st - (k > 0 ? S::STRIDE * 8 : 0));  // next stage's constants: in flight under the products
+            // vector row: P+ c goes to shared memory (corrector sweep), then q = pv+ + P+ c
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                mpc_sts_if(is_vec && ((flags >> (2 + s)) & 1), stn + (S::PC - NU) * 8 + 16 * q + 8 * s, w[VT][s]);
+                w[VT][s] += is_vec ? Pt[VT][s] : 0.0;
+            }
+            // GEMM 2: Mt = Wt [B A] + (H + G | gt)
+            double m[RT][2];
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {
+                mpc_dmma(m[rt][0], m[rt][1], w[rt][0], fb0, cc[rt][0], cc[rt][1]);
+                mpc_dmma(m[rt][0], m[rt][1], w[rt][1], fb1, m[rt][0], m[rt][1]);
+            }
+            finish_stage();
+            // L_uu = chol(M_uu): M_00 lane 0 slot 0; M_10, M_11 lane 4 slots 0, 1
+            const double m00 = __shfl_sync(FULL, m[0][0], 0), m10 = __shfl_sync(FULL, m[0][0], 4), m11 = __shfl_sync(FULL, m[0][1], 4);
+            double t0[RT], t1[RT];
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {  // columns 0, 1 of the own row: slots of the quad's first lane
+                t0[rt] = __shfl_sync(FULL, m[rt][0], lane & ~3);
+                t1[rt] = __shfl_sync(FULL, m[rt][1], lane & ~3);
+            }
+            double il00, rdet;
+            mpc_rsqrt_pair(m00, m11 * m00 - m10 * m10, il00, rdet);
+            const double l10 = m10 * il00;
+            const double il11 = rdet * (m00 * il00);
+            mpc_sts_if(lane0, st + S::LUU * 8, il00);
+            mpc_sts_if(lane0, st + S::LUU * 8 + 8, l10);
+            mpc_sts_if(lane0, st + S::LUU * 8 + 16, il11);
+            // rows of L_xu (x rows), y (vector row): lane (g, q) keeps column q
+            double Lq[RT];
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {
+                const double L0 = t0[rt] * il00;
+                const double L1 = (t1[rt] - L0 * l10) * il11;
+                Lq[rt] = (q == 0) ? L0 : ((q == 1) ? L1 : 0.0);
+                mpc_sts_if(fx[rt] != 0, st + lx_off[rt], Lq[rt]);
+            }
+            // GEMM 3: Pt = Mt - L L'
+#pragma unroll
+            for (int rt = 0; rt < RT; rt++) {
+                mpc_dmma(Pt[rt][0], Pt[rt][1], -Lq[rt], Lq[0], m[rt][0], m[rt][1]);
+#pragma unroll
+                for (int s = 0; s < 2; s++) mpc_sts_if(fl[rt][s] & 16, st + p_off[rt][s], Pt[rt][s]);
+            }
+        }
+    }
+    __syncthreads();
+}
+#endif  // __CUDACC__
+
 // Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PIN.
 template <class CFG>
 MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
@@ -1413,6 +1691,8 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
 
 #if defined(MPC_RICCATI_LANES)
         riccati_factor_lanes<CFG>(sm);  // measured alternative: same throughput, 5 % more solo latency
+#elif defined(__CUDACC__) && !defined(MPC_RICCATI_SERIAL)
+        riccati_factor_mma<CFG>(sm);    // FP64 tensor-core products, one warp (+ backward sweep of the predictor rhs)
 #else
         riccati_factor<CFG>(sm);        // + backward sweep of the predictor right-hand side
 #endif
@@ -1595,18 +1875,6 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
 
     // completeOneIteration (acados_solver_interface.cpp:162-204): cost, trajectories, res_eq
     MPC_PHASE
-    if (state) {  // persist the NLP multipliers; a QP failure clears them, non-finite values are never persisted
-        const bool keep = !(qp_status == 3 || qp_status == 4);
-        for (int it = tid; it < (N + 1) * NX; it += NT) {
-            const double v = sm[(it / NX) * S::STRIDE + S::PI + it % NX];
-            state[it] = (keep && isfinite(v)) ? v : 0.0;
-        }
-        if (NH > 0)
-            for (int it = tid; it < N * NH; it += NT) {
-                const double v = sm[(it / NH) * S::STRIDE + S::LAM + 2 * NZ + it % NH];
-                state[(N + 1) * NX + it] = (keep && isfinite(v)) ? v : 0.0;
-            }
-    }
     {
         double c = 0.0, defect = 0.0;
         if (tid < N) {
@@ -1631,20 +1899,38 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     }
     MPC_PHASE_END
     MPC_PHASE
-    if (tid == 0) {
+    {   // every thread combines the partials (no second barrier) and derives the exit code
         const double pobj = red_get<CFG>(W, 0, 1), res_eq = red_get<CFG>(W, 1, 0);
         int exit_code = 1;
         if (qp_status == 3 || qp_status == 4) exit_code = 4;  // ACADOS_QP_FAILURE
         if (!(res_eq <= L.res_eq_fail) && exit_code == 1) exit_code = 4;  // acados_solver_interface.cpp:176-181
         if (!(pobj == pobj) || isinf(pobj)) exit_code = 4;               // a non-finite objective is never a success
-        info->pobj = pobj;
-        info->res_eq = res_eq;
-        info->res_stat_qp = qp_res[0];
-        info->res_comp_qp = qp_res[1];
-        info->exit_code = exit_code;
-        info->qp_status = qp_status;
-        info->sqp_iter = sqp_iter;
-        info->qp_iter = qp_iter_total;
+        if (tid == 0) {
+            info->pobj = pobj;
+            info->res_eq = res_eq;
+            info->res_stat_qp = qp_res[0];
+            info->res_comp_qp = qp_res[1];
+            info->exit_code = exit_code;
+            info->qp_status = qp_status;
+            info->sqp_iter = sqp_iter;
+            info->qp_iter = qp_iter_total;
+        }
+        if (state) {
+            // Persist the NLP multipliers of this solver slot.  ANY non-success exit clears them: the reference calls
+            // Solver_acados_reset(capsule, 1) + ocp_nlp_solver_reset_qp_memory whenever the exit code is not
+            // ACADOS_SUCCESS -- including the res_eq > 1e-2 demotion (acados_solver_interface.cpp:176-191).
+            // Non-finite values are never persisted.
+            const bool keep = (exit_code == 1);
+            for (int it = tid; it < (N + 1) * NX; it += NT) {
+                const double v = sm[(it / NX) * S::STRIDE + S::PI + it % NX];
+                state[it] = (keep && isfinite(v)) ? v : 0.0;
+            }
+            if (NH > 0)
+                for (int it = tid; it < N * NH; it += NT) {
+                    const double v = sm[(it / NH) * S::STRIDE + S::LAM + 2 * NZ + it % NH];
+                    state[(N + 1) * NX + it] = (keep && isfinite(v)) ? v : 0.0;
+                }
+        }
     }
     MPC_PHASE_END
 #if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)

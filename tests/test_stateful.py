@@ -60,6 +60,42 @@ def test_failed_solve_clears_the_slot():
     assert np.isfinite(se).all() and np.isfinite(st).all()
 
 
+def demoted_batch(spec):
+    """Solves whose single RTI step leaves a dynamics defect above 1e-2: the reference then turns ACADOS_SUCCESS into
+    ACADOS_QP_FAILURE (acados_solver_interface.cpp:176-181) although the QP itself was solved (qp_status 0 or 2)."""
+    import copy
+
+    sp = copy.deepcopy(spec)
+    sp.n_sqp = 1
+    b = scenes.make_scene_batch(sp, 4, 2, seed=8)
+    rng = np.random.default_rng(8)
+    x0 = b["x0"].reshape(8, sp.N + 1, sp.nz).copy()
+    x0[:, 1:, sp.nu + 2] += rng.uniform(-1.5, 1.5, size=x0[:, 1:, 0].shape)  # heading of the warm start far off
+    x0[:, 1:, sp.nu + 3] += rng.uniform(0.0, 1.5, size=x0[:, 1:, 0].shape)   # and its speed
+    return sp, b["xinit"], x0.reshape(8, -1), b["params"]
+
+
+def test_res_eq_demotion_clears_the_slot_too():
+    """the reference resets the solver memory on EVERY non-success exit (Solver_acados_reset(capsule, 1),
+    acados_solver_interface.cpp:183-191), not only on QP failures."""
+    sp, xinit, x0, params = demoted_batch(pb.config_tmpc())
+    st = np.ones((8, oracle.state_size(sp)))
+    _, _, info = oracle.solve_batch(sp, xinit, x0, params, state=st)
+    demoted = [i for i, inf in enumerate(info) if inf["exit_code"] == 4 and inf["qp_status"] in (0, 2)]
+    kept = [i for i, inf in enumerate(info) if inf["exit_code"] == 1]
+    assert demoted, [(i["exit_code"], i["qp_status"], i["res_eq"]) for i in info]
+    for i in demoted:
+        assert info[i]["res_eq"] > 1e-2 and not st[i].any()
+    for i in kept:
+        assert st[i].any()
+    se = np.ones_like(st)
+    _, _, info_e = emu.solve_batch(sp, xinit, x0, params, state=se)
+    assert [i["exit_code"] for i in info_e] == [i["exit_code"] for i in info]
+    for i in demoted:
+        assert not se[i].any()
+    np.testing.assert_allclose(se, st, rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4"])
 def test_gpu_stateful_slots_match_oracle(name):
@@ -87,4 +123,25 @@ def test_gpu_stateful_slots_match_oracle(name):
     np.testing.assert_allclose(fresh_gpu[0][ok], o1[0][ok], rtol=1e-6, atol=1e-6)
     solver.set_state(saved)
     np.testing.assert_array_equal(solver.get_state(), saved)
+    solver.close()
+
+
+@pytest.mark.gpu
+def test_gpu_res_eq_demotion_clears_the_slot():
+    from mpc_planner_b200 import binding
+
+    sp, xinit, x0, params = demoted_batch(pb.config_tmpc())
+    st = np.ones((8, oracle.state_size(sp)))
+    _, _, info = oracle.solve_batch(sp, xinit, x0, params, state=st)
+    solver = binding.BatchSolver(sp, 8)
+    solver.set_stateful(True)
+    solver.set_state(np.ones_like(st))
+    _, _, ginfo, _ = solver.solve(xinit, x0, params)
+    assert [i["exit_code"] for i in ginfo] == [i["exit_code"] for i in info]
+    demoted = [i for i, inf in enumerate(info) if inf["exit_code"] == 4 and inf["qp_status"] in (0, 2)]
+    assert demoted
+    gs = solver.get_state()
+    for i in demoted:
+        assert not gs[i].any()
+    np.testing.assert_allclose(gs, st, rtol=1e-5, atol=1e-6)
     solver.close()
