@@ -142,7 +142,10 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
                       int *best);
 
 /* Device-buffer path: same arrays already resident in HBM; asynchronous on `stream`
- * (a cudaStream_t passed as void*; NULL = default stream). */
+ * (a cudaStream_t passed as void*; NULL = default stream).  The call selects the handle's device.  It uses the
+ * handle's scratch buffers (transposed parameters, persistent multipliers, timing events): ONE solve call may be in
+ * flight per handle -- enqueue calls of one handle on one stream, or synchronise between streams; independent
+ * concurrent solves need separate handles (as every reference `Solver` instance has its own acados memory). */
 int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const double *d_x0,
                         const double *d_params, double *d_xtraj, double *d_utraj,
                         mpcgpu_info *d_info, int *d_best, void *stream);
@@ -153,7 +156,9 @@ int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const dou
  * projectToSafety / setParameters in topology mode (linearized_constraints.cpp:49-189).
  *   xinit[S*nx], x0[S*G*(nu+nx)*(N+1)] (the guesses' warm starts = guidance trajectories),
  *   scene_params[S*N*npar]: the MAIN solver's parameters of each control step (weights, spline, obstacle
- *       predictions; the lin_constraint slots are ignored) -- uploaded once per step, not once per guess;
+ *       predictions; of the lin_constraint slots only the rows behind the obstacles are read: static halfspaces of
+ *       guided planners, linearized_constraints.cpp:111-123 -- dummies (1, 0, x0 + 100) if there are none) -- uploaded
+ *       once per step, not once per guess;
  *   guided[G]: 1 = guided planner (halfspaces a = (o - p)/|o - p|, b = a.o - (1e-3 + robot_radius) from its warm
  *       start p_k, after projecting p_k out of the obstacle discs), 0 = non-guided planner (dummy halfspaces
  *       (1, 0, x0 + 100) everywhere); stage 0 always gets the dummies.
@@ -182,9 +187,11 @@ int mpcgpu_set_group(mpcgpu_handle h, int group);
 
 /* Solver::solve()'s timeout (mpc_planner_solver/src/acados_solver_interface.cpp:91-117, `_params.solver_timeout`,
  * set per control step at mpc_planner/src/planner.cpp:118 and guidance_constraints.cpp:258,333): after each SQP-RTI
- * iteration a solve stops iterating once (time since the start of THIS solve) + (its average iteration time) >= seconds,
+ * iteration a solve stops iterating once (time since the start of the CALL) + (its average iteration time) >= seconds,
  * then completes as usual (trajectories, cost, exit code; mpcgpu_info.sqp_iter tells how many iterations ran).  Time is
- * read on the device (%globaltimer) per solve; it applies to every following solve call on the handle.
+ * read on the device (%globaltimer): the call's clock starts in its first kernel (parameter transposition / packing, i.e.
+ * after the host-to-device copies of the host path have landed), so the later waves of a batch larger than the GPU holds at
+ * once do not get a fresh budget; it applies to every following solve call on the handle.
  * seconds <= 0 disables the check (default) -- note that the reference with solver_timeout = 0 stops after one iteration. */
 int mpcgpu_set_timeout(mpcgpu_handle h, double seconds);
 

@@ -42,7 +42,16 @@ thread_local char g_last_cuda_error[256] = "";
 // kernels
 // ---------------------------------------------------------------------------------------------
 // params[P][N][npar] (AcadosParameters::all_parameters, stage-major) -> pt[P][npar][pt_stride(N)]
-__global__ void transpose_params_kernel(const double *__restrict__ params, double *__restrict__ pt, int P, int N, int npar) {
+__device__ __forceinline__ void stamp_call_start(long long *t_call) {
+    if (t_call && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        *t_call = (long long)t;
+    }
+}
+
+__global__ void transpose_params_kernel(const double *__restrict__ params, double *__restrict__ pt, int P, int N, int npar, long long *t_call) {
+    stamp_call_start(t_call);
     const long long total = (long long)P * N * npar;
     const int PT = pt_stride(N);
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -63,7 +72,8 @@ __global__ void transpose_params_kernel(const double *__restrict__ params, doubl
 __global__ void pack_tmpc_kernel(const double *__restrict__ scene_params, const double *__restrict__ xinit_scene,
                                  const double *__restrict__ x0, const int *__restrict__ guided, double *__restrict__ pt,
                                  double *__restrict__ xinit_out, int S, int G, int N, int npar, int nx, int nu, int lin0, int n_lin,
-                                 int obs0, int obs_stride, int n_obs, double robot_radius) {
+                                 int obs0, int obs_stride, int n_obs, double robot_radius, long long *t_call) {
+    stamp_call_start(t_call);
     const int p = blockIdx.x, s = p / G, g = p - s * G;
     if (s >= S) return;
     const double *sp = scene_params + (size_t)s * N * npar;
@@ -99,10 +109,18 @@ __global__ void pack_tmpc_kernel(const double *__restrict__ scene_params, const 
             double a1 = 1.0, a2 = 0.0, b = x_init + 100.0;  // dummies (linearized_constraints.cpp:53,155-166,181-187)
             if (build && j < n_obs) {
                 const double ox = sp[k * npar + obs0 + obs_stride * j], oy = sp[k * npar + obs0 + obs_stride * j + 1];
-                const double dx = ox - px, dy = oy - py, dist = sqrt(dx * dx + dy * dy);
+                double dx = ox - px, dy = oy - py, dist = sqrt(dx * dx + dy * dy);
+                if (dist < 1e-9) { dx = 1.0; dy = 0.0; dist = 1.0; }  // same guard as the projection: never a NaN normal
                 a1 = dx / dist;
                 a2 = dy / dist;
                 b = a1 * ox + a2 * oy - R;
+            } else if (build) {
+                // rows behind the obstacles: the static / road halfspaces that LinearizedConstraints::update copies into the
+                // `_n_other_halfspaces` rows (linearized_constraints.cpp:111-123) -- taken from the control step's own
+                // parameter block (callers without static halfspaces leave the dummies there)
+                a1 = sp[k * npar + lin0 + 3 * j];
+                a2 = sp[k * npar + lin0 + 3 * j + 1];
+                b = sp[k * npar + lin0 + 3 * j + 2];
             }
             ptp[(lin0 + 3 * j) * PT + k] = a1;
             ptp[(lin0 + 3 * j + 1) * PT + k] = a2;
@@ -238,6 +256,49 @@ const KernelTable *find_kernel(const mpcgpu_problem_desc &d) {
 
 }  // namespace
 
+// Range checks of everything the kernels index with: a wrong descriptor must be refused at the ABI, not read out of bounds
+// on the device (parameters are fetched as __ldg(base + index * stride + stage)).
+static bool desc_is_valid(const mpcgpu_problem_desc &d) {
+    const int nz = d.nx + d.nu;
+    if (d.N < 1 || d.N + 1 > 32 || d.nx <= 0 || d.nu <= 0 || nz > MPCGPU_MAX_NZ || d.npar <= 0 || d.nh < 0) return false;
+    if (!(d.dt > 0.0) || d.n_sqp < 1 || d.qp_iter_max < 0 || !(d.qp_tol > 0.0) || !(d.reg_epsilon > 0.0)) return false;
+    if (!(d.qp_mu0 > 0.0) || !(d.qp_thr0 > 0.0) || !(d.qp_relax >= 0.0) || !(d.res_eq_fail > 0.0)) return false;
+    if (d.qp_warm_start != 0 && (!(d.qp_ws_thr > 0.0) || !(d.qp_ws_mu > 0.0))) return false;
+    auto in_range = [&](int idx, int extent) { return idx >= 0 && extent >= 1 && idx + extent <= d.npar; };
+    auto optional = [&](int idx) { return idx == -1 || in_range(idx, 1); };
+    if (!in_range(d.p_acceleration, 1) || !in_range(d.p_angular_velocity, 1)) return false;
+    if (!optional(d.p_slack) || !optional(d.p_ego_disc_offset)) return false;
+    const bool needs_vref = d.weigh_velocity != 0 || d.objective == MPCGPU_OBJ_CURVATURE_AWARE;
+    if (needs_vref ? (!in_range(d.p_velocity, 1) || !in_range(d.p_reference_velocity, 1))
+                   : (!optional(d.p_velocity) || !optional(d.p_reference_velocity))) return false;
+    if (!in_range(d.p_contour, 1)) return false;
+    if (d.objective == MPCGPU_OBJ_CONTOURING ? !in_range(d.p_lag, 1) : !optional(d.p_lag)) return false;
+    if (d.n_segments < 1 || !in_range(d.p_spline, 9 * d.n_segments)) return false;
+    if (d.n_con_modules < 0 || d.n_con_modules > 3) return false;
+    int rows = 0;
+    bool needs_disc = false;
+    for (int m = 0; m < d.n_con_modules; m++) {
+        int stride = 3;
+        switch (d.con_kind[m]) {
+        case MPCGPU_CON_LINEAR: break;
+        case MPCGPU_CON_ELLIPSOID: stride = 7; needs_disc = true; break;
+        case MPCGPU_CON_GAUSSIAN: stride = 6; needs_disc = true; break;
+        case MPCGPU_CON_DECOMP:
+        case MPCGPU_CON_SCENARIO: break;
+        default: return false;
+        }
+        if (d.con_count[m] < 1 || !in_range(d.con_param[m], stride * d.con_count[m])) return false;
+        rows += d.con_count[m];
+    }
+    if (rows != d.nh) return false;
+    if (needs_disc && !in_range(d.p_ego_disc_radius, 1)) return false;
+    for (int i = 0; i < nz; i++) {
+        if (d.lower_bound[i] != d.lower_bound[i] || d.upper_bound[i] != d.upper_bound[i]) return false;
+        if (!(d.lower_bound[i] <= d.upper_bound[i])) return false;
+    }
+    return true;
+}
+
 struct mpcgpu_solver {
     mpcgpu_problem_desc desc;
     Layout layout;
@@ -252,6 +313,7 @@ struct mpcgpu_solver {
     int *d_best;
     unsigned int *d_sm_slots;  // per-SM tickets (see sqp_kernel)
     double *d_state;           // persistent NLP multipliers per solve slot (mpcgpu_set_stateful), else null
+    long long *d_t_call;       // per chunk: %globaltimer at the first kernel of the call (solver timeout)
     size_t n_state;
     int *d_guided;             // T-MPC guided flags (lazy)
     double *d_xinit_scene;     // T-MPC per-control-step initial states (lazy)
@@ -295,6 +357,7 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     *out = nullptr;
     const KernelTable *kt = find_kernel(*desc);
     if (!kt) return MPCGPU_ERR_UNSUPPORTED;
+    if (!desc_is_valid(*desc)) return MPCGPU_ERR_ARG;
     if (mpcgpu_device_count() <= device || device < 0) return MPCGPU_ERR_NO_DEVICE;
     CUDA_TRY(cudaSetDevice(device));
     mpcgpu_solver *h = new (std::nothrow) mpcgpu_solver();
@@ -336,6 +399,7 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     ok = ok && cudaMalloc(&h->d_info, B * sizeof(mpcgpu_info)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_best, B * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_sm_slots, 256 * sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_t_call, 8 * sizeof(long long)) == cudaSuccess;
     if (ok) ok = cudaMemset(h->d_sm_slots, 0, 256 * sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
     if (ok) ok = cudaMemset(h->d_pt, 0, B * (size_t)desc->npar * pt_stride(desc->N) * sizeof(double)) == cudaSuccess;
@@ -360,6 +424,7 @@ int mpcgpu_destroy(mpcgpu_handle h) {
     cudaFree(h->d_info);
     cudaFree(h->d_best);
     cudaFree(h->d_sm_slots);
+    cudaFree(h->d_t_call);
     cudaFree(h->d_state);
     cudaFree(h->d_guided);
     cudaFree(h->d_xinit_scene);
@@ -379,15 +444,18 @@ int mpcgpu_destroy(mpcgpu_handle h) {
 
 // enqueue transpose -> sqp -> select_best for `count` solves whose scratch slot starts at `slot`
 static int enqueue_solve(mpcgpu_handle h, int slot, int count, const double *d_xinit, const double *d_x0, const double *d_params,
-                         double *d_xtraj, double *d_utraj, mpcgpu_info *d_info, int *d_best, cudaStream_t s, bool timed) {
+                         double *d_xtraj, double *d_utraj, mpcgpu_info *d_info, int *d_best, cudaStream_t s, bool timed, int chunk = 0) {
     const int N = h->desc.N, npar = h->desc.npar;
     double *pt = h->d_pt + (size_t)slot * npar * pt_stride(N);
     const long long total = (long long)count * N * npar;
     int tb = (int)((total + 255) / 256);
     if (tb > 148 * 16) tb = 148 * 16;
-    transpose_params_kernel<<<tb, 256, 0, s>>>(d_params, pt, count, N, npar);
+    long long *t_call = (h->layout.timeout_s > 0.0) ? h->d_t_call + chunk : nullptr;
+    transpose_params_kernel<<<tb, 256, 0, s>>>(d_params, pt, count, N, npar, t_call);
     if (timed) cudaEventRecord(h->ev0, s);
-    h->kt->launch_sqp(h->layout, count, d_xinit, d_x0, pt, d_xtraj, d_utraj, d_info, h->d_sm_slots,
+    Layout L = h->layout;
+    L.t_call = t_call;
+    h->kt->launch_sqp(L, count, d_xinit, d_x0, pt, d_xtraj, d_utraj, d_info, h->d_sm_slots,
                       h->d_state ? h->d_state + (size_t)slot * h->n_state : nullptr, h->kt->smem_bytes, s);
     if (timed) cudaEventRecord(h->ev1, s);
     h->launches += 2;
@@ -404,6 +472,7 @@ int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const dou
                         double *d_xtraj, double *d_utraj, mpcgpu_info *d_info, int *d_best, void *stream) {
     if (!h || P <= 0 || !d_xinit || !d_x0 || !d_params || !d_xtraj || !d_utraj || !d_info) return MPCGPU_ERR_ARG;
     if (P > h->max_batch) return MPCGPU_ERR_BATCH;
+    CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     int rc = enqueue_solve(h, 0, P, d_xinit, d_x0, d_params, d_xtraj, d_utraj, d_info, d_best, s, h->timing != 0);
     if (rc != MPCGPU_OK) return rc;
@@ -442,7 +511,7 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
                                                               // chunk overlaps the first wave of the next
         CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
         int rc = enqueue_solve(h, (int)o, (int)n, h->d_xinit + o * h->n_xinit, h->d_x0 + o * h->n_x0, h->d_params + o * h->n_params,
-                               h->d_xtraj + o * h->n_xtraj, h->d_utraj + o * h->n_utraj, h->d_info + o, h->d_best + o / group, sc, h->timing != 0 && n_chunks == 1);
+                               h->d_xtraj + o * h->n_xtraj, h->d_utraj + o * h->n_utraj, h->d_info + o, h->d_best + o / group, sc, h->timing != 0 && n_chunks == 1, c);
         if (rc != MPCGPU_OK) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_cmp[c], sc));
         CUDA_TRY(cudaStreamWaitEvent(h->stream_out, h->ev_cmp[c], 0));
@@ -513,10 +582,13 @@ int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, c
         CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
         pack_tmpc_kernel<<<(unsigned)np, 128, 0, sc>>>(h->d_params + s0 * h->n_params, h->d_xinit_scene + s0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_guided,
                                                        h->d_pt + p0 * (size_t)d.npar * pt_stride(d.N), h->d_xinit + p0 * h->n_xinit, (int)ns, G, d.N, d.npar, d.nx, d.nu,
-                                                       d.con_param[m_lin], d.con_count[m_lin], d.con_param[m_obs], obs_stride, n_obs, robot_radius);
+                                                       d.con_param[m_lin], d.con_count[m_lin], d.con_param[m_obs], obs_stride, n_obs, robot_radius,
+                                                       (h->layout.timeout_s > 0.0) ? h->d_t_call + c : nullptr);
         const bool timed = h->timing != 0 && n_chunks == 1;
         if (timed) cudaEventRecord(h->ev0, sc);
-        h->kt->launch_sqp(h->layout, (int)np, h->d_xinit + p0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_pt + p0 * (size_t)d.npar * pt_stride(d.N),
+        Layout L = h->layout;
+        L.t_call = (h->layout.timeout_s > 0.0) ? h->d_t_call + c : nullptr;
+        h->kt->launch_sqp(L, (int)np, h->d_xinit + p0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_pt + p0 * (size_t)d.npar * pt_stride(d.N),
                           h->d_xtraj + p0 * h->n_xtraj, h->d_utraj + p0 * h->n_utraj, h->d_info + p0, h->d_sm_slots,
                           h->d_state ? h->d_state + p0 * h->n_state : nullptr, h->kt->smem_bytes, sc);
         if (timed) cudaEventRecord(h->ev1, sc);

@@ -79,6 +79,7 @@ inline Layout make_layout(const mpcgpu_problem_desc &d) {
     L.qp_ws_mu = d.qp_ws_mu;
     L.qp_relax = d.qp_relax;
     L.timeout_s = 0.0;  // mpcgpu_set_timeout
+    L.t_call = nullptr;
     return L;
 }
 

@@ -1796,8 +1796,10 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     // through shared memory with the barrier that ends the step phase.
     long long t_solve0 = 0, t_iter0 = 0, t_iters = 0;
     if (L.timeout_s > 0.0) {
-        t_solve0 = mpc_clock_ns();
-        t_iter0 = t_solve0;
+        t_iter0 = mpc_clock_ns();
+        // the budget runs from the start of the CALL (first kernel of the launch sequence) when the host layer provides
+        // that timestamp: solves of a later wave of a large batch do not get a fresh budget
+        t_solve0 = L.t_call ? *L.t_call : t_iter0;
     }
 #if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
     if (threadIdx.x == 0) {

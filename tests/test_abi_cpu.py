@@ -68,3 +68,34 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
                 assert "tests.emu" not in text and "libmpcgpu_emu" not in text, f
+
+
+@pytest.mark.parametrize("name", list(pb.CONFIGS))
+def test_descriptor_validation_accepts_the_shipped_stacks(lib, name):
+    """mpcgpu_create range-checks every parameter index / block extent against npar before it looks for a device
+    (a wrong descriptor must be refused at the ABI, not read out of bounds by the kernel)."""
+    if lib.mpcgpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    d = pb.CONFIGS[name]().desc()
+    if not lib.mpcgpu_problem_supported(ctypes.byref(d)):
+        pytest.skip("oracle-only stack")
+    h = ctypes.c_void_p()
+    rc = lib.mpcgpu_create(ctypes.byref(d), 0, 4, ctypes.byref(h))
+    assert b"no CUDA device" in lib.mpcgpu_strerror(rc), lib.mpcgpu_strerror(rc)
+
+
+@pytest.mark.parametrize("field,value", [("p_spline", 130), ("p_ego_disc_radius", -1), ("p_contour", 135), ("dt", 0.0), ("n_sqp", 0),
+                                         ("npar", 100), ("p_acceleration", -1), ("qp_tol", 0.0)])
+def test_descriptor_validation_rejects_out_of_range_indices(lib, field, value):
+    d = pb.config_tmpc().desc()
+    setattr(d, field, value)
+    h = ctypes.c_void_p()
+    rc = lib.mpcgpu_create(ctypes.byref(d), 0, 4, ctypes.byref(h))
+    assert lib.mpcgpu_strerror(rc) == b"invalid argument", (field, lib.mpcgpu_strerror(rc))
+    # a constraint block that runs past the end of the parameter vector
+    d = pb.config_tmpc().desc()
+    d.con_param[1] = d.npar - 10
+    assert lib.mpcgpu_strerror(lib.mpcgpu_create(ctypes.byref(d), 0, 4, ctypes.byref(h))) == b"invalid argument"
+    d = pb.config_tmpc().desc()
+    d.lower_bound[0] = float("nan")
+    assert lib.mpcgpu_strerror(lib.mpcgpu_create(ctypes.byref(d), 0, 4, ctypes.byref(h))) == b"invalid argument"
