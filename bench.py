@@ -38,30 +38,63 @@ GUESSES = 8
 ALG_BYTES_PER_SOLVE = 22816 + 1224  # xinit + x0 + all_parameters in, xtraj + utraj + info out
 
 
-def flops_per_solve(spec, mean_qp_iter, n_sqp):
-    """Algorithmic FLOP model of one solve (DESIGN.md 'FLOP model'): counted from the kernel's
-    arithmetic, FMA = 2 flops, sparse structure not discounted."""
-    nx, nu, nz, nh, N = spec.nx, spec.nu, spec.nz, spec.nh, spec.N
-    nrow = 2 * nz + nh
-    f_factor = (nz * (nz + 1) // 2) * (nx * nx + nx) * 2 + (nx * (nx + 1) // 2) * 8 + nx * nx * 2
-    f_solve = 2 * ((nz * nx + nx * nu * 2) * 2 + (nx * nu * 2 + nx * nz + nx * nx) * 2)
-    f_rows = nrow * (14 + 2 * 12 + 10 + 12)
-    f_resid = (nz * nz + 2 * nx * nz) * 2 + nrow * 8
-    f_ipm = f_factor + f_solve + f_rows + f_resid
-    f_lin = 3000 + 60 * nh + 2 * nz ** 3 // 3
-    return N * (n_sqp * f_lin + mean_qp_iter * f_ipm)
+def flop_counts():
+    """FLOPs per SQP-RTI iteration / per interior-point iteration / fixed, MEASURED from the kernel source by
+    scripts/count_flops.py (host emulation of csrc/*.cuh with a counting `double`; profiles/r02_flops.json)."""
+    with open(os.path.join(ROOT, "profiles", "r02_flops.json")) as f:
+        return json.load(f)
+
+
+def flops_per_solve(mean_sqp_iter, mean_qp_iter):
+    fc = flop_counts()
+    return mean_sqp_iter * fc["per_sqp_iteration"] + mean_qp_iter * fc["per_ipm_iteration"] + fc["per_solve_fixed"]
 
 
 def make_batch(spec, n_scenes, seed):
-    """n_scenes x 8 guesses; a pool of distinct scenes is generated and tiled (generation is
-    host-side numpy and not part of the measured path)."""
-    pool = min(n_scenes, 64)
-    base = scenes.make_scene_batch(spec, pool, GUESSES, seed=seed)
-    reps = (n_scenes + pool - 1) // pool
-    out = {}
-    for k in ("xinit", "x0", "params"):
-        out[k] = np.ascontiguousarray(np.tile(base[k], (reps, 1))[: n_scenes * GUESSES])
-    return out
+    """n_scenes DISTINCT scenes x 8 guesses (scenes.make_scene_batch_chunked: chunk c of 16 scenes is seeded with
+    seed * 100003 + c, so the first k chunks of a larger batch ARE the smaller batch -- the CPU arm's bounded sample is a
+    prefix of the GPU arm's batch).  Generation is host-side numpy and not part of the measured path."""
+    return scenes.make_scene_batch_chunked(spec, n_scenes, GUESSES, seed=seed)
+
+
+def rotated(batch, n_scenes, j, nsets):
+    """Set j of the rotating inputs: the same scenes rolled by j/nsets of the batch (other addresses, cold in L2)."""
+    sh = (n_scenes * j // nsets) * GUESSES
+    return {k: np.ascontiguousarray(np.roll(v, sh, axis=0)) for k, v in batch.items()}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and therefore its pinned staging buffers, first touch) to the NUMA node its GPU hangs off:
+    with 8 ranks the host-buffer path otherwise crosses the socket interconnect for half of the GPUs."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
 
 
 class ClockSampler:
@@ -142,26 +175,21 @@ def cpu_solve_pass(spec, batch, n_solves, threads):
     return time.perf_counter() - t, info
 
 
-def calibrate_threads(spec, batch):
-    """Pick the OpenMP thread count that solves a small sample fastest (hyper-threads / cgroup quotas
-    make 'all logical CPUs' a bad default on some boxes)."""
-    cores = usable_cores()
-    cands = sorted({cores, max(1, cores // 2)}, reverse=True)
-    best_t, best_rate = cands[0], 0.0
-    for t in cands:
-        n = len(batch["xinit"])  # the whole pool: small samples are dominated by the slowest solve
-        cpu_solve_pass(spec, batch, min(n, t), t)  # spin the team up
-        dt, _ = cpu_solve_pass(spec, batch, n, t)
-        if n / dt > best_rate:
-            best_t, best_rate = t, n / dt
-    return best_t
+def cpu_threads():
+    """Thread rule of the CPU arm: every core this process may run on (no racing between candidate counts)."""
+    return usable_cores()
 
 
-def cpu_arm(spec, target_seconds=12.0, pool_scenes=64, seed=2024):
-    """The CPU arm: acados-equivalent oracle, OpenMP over the batch, bounded sample of the workload."""
-    batch = make_batch(spec, pool_scenes, seed=seed)
+REF_SCENES = int(os.environ.get("MPC_BENCH_REF_SCENES", "64"))  # bounded CPU sample: the first 64 scenes (512 solves) of the step
+
+
+def cpu_arm(spec, target_seconds=12.0):
+    """The CPU arm inside the B200 run: acados-equivalent oracle, OpenMP over the batch, on a PREFIX of the GPU arm's own
+    batch (rank 0, set 0)."""
+    batch = make_batch(spec, REF_SCENES, seed=1)
     n = len(batch["xinit"])
-    threads = calibrate_threads(spec, batch)
+    threads = cpu_threads()
+    cpu_solve_pass(spec, batch, min(n, 2 * threads), threads)  # spin the team up
     total, t0 = 0, time.perf_counter()
     while True:
         cpu_solve_pass(spec, batch, n, threads)
@@ -173,16 +201,17 @@ def cpu_arm(spec, target_seconds=12.0, pool_scenes=64, seed=2024):
 
 
 def run_reference(args, spec):
-    """--impl reference: the CPU implementation of the path (acados itself cannot be built here:
-    un-pinned third-party HEAD, absent from /root/reference; the arm runs the acados-equivalent
-    oracle port with the host threads that serve it best).  Rank 0 only."""
+    """--impl reference: the CPU implementation of the path (acados itself cannot be built here: un-pinned third-party
+    HEAD, absent from /root/reference; the arm runs the acados-equivalent oracle port on every usable host core).  Same
+    config as the B200 arm; each step is a bounded sample of that workload: the first REF_SCENES scenes of the step's
+    batch (identical bytes: the generator is prefix-stable).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pool = int(os.environ.get("MPC_BENCH_REF_SCENES", "64"))
-    batch = make_batch(spec, pool, seed=2024)
+    n_scenes = min(REF_SCENES, args.scenes)
+    batch = make_batch(spec, n_scenes, seed=1)
     sample = len(batch["xinit"])
-    threads = calibrate_threads(spec, batch)
+    threads = cpu_threads()
     for _ in range(args.warmup):
         cpu_solve_pass(spec, batch, min(sample, 2 * threads), threads)
     t0 = time.perf_counter()
@@ -194,9 +223,10 @@ def run_reference(args, spec):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(sample // GUESSES), "sample": f"{sample} solves per step (bounded CPU sample of the same workload)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} solves/step x {args.steps} steps in {dt:.2f} s, OpenMP over the batch ({threads} threads of {usable_cores()} usable CPUs), acados-equivalent CPU restatement (oracle/), not acados"},
+        "config": bench_config(args.scenes),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(), "nproc": os.cpu_count(),
+                         "sample": f"the first {n_scenes} scenes = {sample} solves of the step's batch (same seeds as the B200 arm's rank 0), x {args.steps} steps in {dt:.2f} s; "
+                                   f"OpenMP over the batch, {threads} threads = every usable CPU; acados-equivalent CPU restatement (oracle/), not acados"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,7 +235,102 @@ def run_reference(args, spec):
 
 def workload_name(n_scenes):
     return (f"BASELINE configs[1]: T-MPC++ P=8 guesses, N=20, 8 dynamic obstacles (unicycle nx=5 nu=2, npar=135, nh=16), "
-            f"{n_scenes} scenes x 8 guesses = {n_scenes * GUESSES} solves per step per GPU, 10 SQP-RTI iterations per solve")
+            f"{n_scenes} distinct scenes x 8 guesses = {n_scenes * GUESSES} solves per step per GPU, 10 SQP-RTI iterations per solve")
+
+
+def bench_config(n_scenes):
+    """The part of `config` both arms print identically."""
+    return {"workload": workload_name(n_scenes), "solves_per_step_per_gpu": n_scenes * GUESSES,
+            "scenes": "scenes.make_scene_batch_chunked(config_tmpc, n_scenes, 8, seed = 1 + rank)", "l2": "inputs larger than L2: 4 rotating resident input sets of 93 MB (the step's scenes rolled by a quarter of the batch each)"}
+
+
+def run_sharded(args, spec, rank, world, local_rank, dist):
+    """BASELINE configs[4]: ONE T-MPC++ control step with P guesses, split over the GPUs in contiguous blocks; the timed
+    region holds the local solves AND the NCCL best-trajectory reduction (mpcgpu_dist_solve_tmpc_device, include/
+    mpcgpu_dist.h).  Checks: the winner is identical on every rank and equals the winner of the same step solved on one
+    GPU.  Prints one JSON line (rank 0) with a row per P."""
+    import torch
+
+    from mpc_planner_b200 import binding, dist as mdist
+
+    dev = torch.device("cuda", local_rank)
+    N, nx, nu, nz = spec.N, spec.nx, spec.nu, spec.nz
+    Ps = [int(p) for p in args.guesses.split(",")]
+    Pmax = max(Ps)
+    uid = torch.zeros(mdist.ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(mdist.unique_id()), dtype=torch.uint8))
+    if dist is not None:
+        dist.broadcast(uid, src=0)
+    solver = binding.BatchSolver(spec, max_batch=Pmax, device=local_rank)
+    sh = mdist.ShardedTMPC(solver, rank, world, bytes(uid.cpu().numpy().tobytes()))
+    stream = torch.cuda.current_stream(dev)
+    rows = []
+    for P in Ps:
+        if P % world != 0:
+            continue
+        G = P // world
+        g0 = rank * G
+        step = make_step(spec, P)
+        loc = {k: torch.from_numpy(np.ascontiguousarray(step[k][g0:g0 + G])).to(dev) for k in ("xinit", "x0", "params")}
+        d_xt = torch.empty((G, N + 1, nx), dtype=torch.float64, device=dev)
+        d_ut = torch.empty((G, N, nu), dtype=torch.float64, device=dev)
+        d_info = torch.empty((G, binding.INFO_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        d_best = torch.full((1,), -7, dtype=torch.int32, device=dev)
+        w_xt = torch.zeros((N + 1, nx), dtype=torch.float64, device=dev)
+        w_ut = torch.zeros((N, nu), dtype=torch.float64, device=dev)
+        w_info = torch.zeros((binding.INFO_DTYPE.itemsize,), dtype=torch.uint8, device=dev)
+
+        def control_step():
+            sh.solve_device(1, G, g0, loc["xinit"].data_ptr(), loc["x0"].data_ptr(), loc["params"].data_ptr(), d_xt.data_ptr(), d_ut.data_ptr(),
+                            d_info.data_ptr(), d_best.data_ptr(), w_xt.data_ptr(), w_ut.data_ptr(), w_info.data_ptr(), stream.cuda_stream)
+
+        for _ in range(max(args.warmup, 3)):
+            control_step()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            control_step()
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # ---- checks: same winner everywhere, equal to the single-GPU winner of the whole step ----
+        best = int(d_best.item())
+        rec = torch.cat([torch.tensor([float(best)], dtype=torch.float64, device=dev), w_xt.flatten(), w_ut.flatten()])
+        recs = [torch.empty_like(rec) for _ in range(world)]
+        if dist is not None:
+            dist.all_gather(recs, rec)
+        else:
+            recs = [rec]
+        same_everywhere = all(bool(torch.equal(recs[0], r)) for r in recs)
+        equal_single = None
+        if rank == 0:
+            full = binding.BatchSolver(spec, max_batch=P, device=local_rank)
+            fx, fu, finfo, fbest = full.solve(step["xinit"], step["x0"], step["params"])
+            full.close()
+            equal_single = bool(fbest == best and (best < 0 or (np.array_equal(fx[best], w_xt.cpu().numpy()) and np.array_equal(fu[best], w_ut.cpu().numpy()))))
+        rows.append({"P": P, "gpus": world, "guesses_per_gpu": G, "latency_ms": ms, "solves_per_s": P / (ms * 1e-3), "winner": best,
+                     "identical_on_every_rank": same_everywhere, "equals_single_gpu_winner": equal_single})
+    sh.close()
+    solver.close()
+    if rank == 0:
+        print(json.dumps({"mode": "sharded", "metric": "control-step latency / solves per second of ONE T-MPC++ step, P guesses split over the GPUs",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "dtype": "f64", "data": "synthetic",
+                          "collective": "ncclAllGather (16 B/rank) + ncclAllReduce (winner record, 1.3 KB) inside the timed region, CUDA events, max over ranks",
+                          "rows": rows}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def make_step(spec, P):
+    """One control step (one scene) with P guesses: chunks of 8 guesses of the same scene generator (seed 7)."""
+    return scenes.make_scene_batch(spec, 1, P, seed=7)
 
 
 def main():
@@ -216,6 +341,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenes", type=int, default=int(os.environ.get("MPC_BENCH_SCENES", "512")), help="scenes per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="throughput", choices=["throughput", "sharded"],
+                    help="throughput: independent scenes per GPU (the contract line); sharded: ONE control step whose P guesses are "
+                         "split over the GPUs, NCCL best-trajectory reduction inside the timed region (BASELINE configs[4])")
+    ap.add_argument("--guesses", default="8,64,512,4096", help="sharded mode: total guesses P of the control step (comma list)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -232,6 +361,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -241,6 +371,10 @@ def main():
 
     from mpc_planner_b200 import binding
 
+    if args.mode == "sharded":
+        run_sharded(args, spec, rank, world, local_rank, dist)
+        return
+
     S, P = args.scenes, args.scenes * GUESSES
     N, nx, nu, nz, npar = spec.N, spec.nx, spec.nu, spec.nz, spec.npar
     solver = binding.BatchSolver(spec, max_batch=P, device=local_rank)
@@ -249,7 +383,8 @@ def main():
     # ---- inputs: NSETS distinct batches resident in HBM; rotating through them makes every step's
     # inputs cold in L2 (NSETS x 93 MB > 126 MB L2) ----
     NSETS = 4
-    host_sets = [make_batch(spec, S, seed=1000 * rank + 17 * j + 1) for j in range(NSETS)]
+    base_set = make_batch(spec, S, seed=1 + rank)  # S distinct scenes; rank 0's set 0 is what the CPU arm samples
+    host_sets = [rotated(base_set, S, j, NSETS) for j in range(NSETS)]
     dev = torch.device("cuda", local_rank)
     d_sets = []
     for hs in host_sets:
@@ -301,7 +436,27 @@ def main():
     # per-solve statistics of the last step (for the FLOP model)
     info = np.frombuffer(d_info.cpu().numpy().tobytes(), dtype=binding.INFO_DTYPE)
     mean_qp_iter = float(info["qp_iter"].mean())
+    mean_sqp_iter = float(info["sqp_iter"].mean())
     frac_success = float((info["exit_code"] == 1).mean())
+
+    # ---- how many of the solves are converged after the reference's 10 RTI steps?  Same algorithm run for 40 steps on a
+    # sample (the first 512 solves of set 0); converged = feasible in both runs and trajectories equal to 1e-4 relative.
+    # A 1e-4 comparison with any other SQP-RTI implementation (acados) is only meaningful on this subset. ----
+    import copy
+
+    spec40 = copy.deepcopy(spec)
+    spec40.n_sqp = 40
+    n_cv = min(P, 512)
+    cv = {k: host_sets[0][k][:n_cv] for k in ("xinit", "x0", "params")}
+    s10 = binding.BatchSolver(spec, max_batch=n_cv, device=local_rank)
+    s40 = binding.BatchSolver(spec40, max_batch=n_cv, device=local_rank)
+    x10, _, i10, _ = s10.solve(cv["xinit"], cv["x0"], cv["params"])
+    x40, _, i40, _ = s40.solve(cv["xinit"], cv["x0"], cv["params"])
+    s10.close()
+    s40.close()
+    both = np.array([a["exit_code"] == 1 and b["exit_code"] == 1 for a, b in zip(i10, i40)])
+    rel = np.abs(x10 - x40).reshape(n_cv, -1).max(axis=1) / (1.0 + np.abs(x40).reshape(n_cv, -1).max(axis=1))
+    converged_fraction = float((rel[both] <= 1e-4).mean()) if both.any() else 0.0
 
     # ---- kernel-only duration (CUDA events on the launching stream around the SQP kernel) ----
     solver.set_timing(True)
@@ -412,37 +567,46 @@ def main():
         hbm_peak, peak_src = measured_peaks()
         fp64_peak = float(lib.mpcgpu_measure_fp64_gflops(local_rank))
         achieved_gbs = ALG_BYTES_PER_SOLVE * P / (kernel_ms * 1e-3) / 1e9
-        fl = flops_per_solve(spec, mean_qp_iter, spec.n_sqp)
+        fl = flops_per_solve(mean_sqp_iter, mean_qp_iter)
         achieved_gflops = fl * P / (kernel_ms * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu_baseline:
             v, threads, n_cpu, dt = cpu_arm(spec, target_seconds=float(os.environ.get("MPC_BENCH_CPU_SECONDS", "12")))
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{n_cpu} solves of the same workload in {dt:.1f} s, OpenMP over the batch ({threads} threads of {usable_cores()} usable CPUs); acados-equivalent CPU restatement (oracle/), not acados"}
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(), "nproc": os.cpu_count(),
+                   "sample": f"{n_cpu} solves in {dt:.1f} s: repeated passes over the first {REF_SCENES} scenes = {REF_SCENES * GUESSES} solves of this step's batch (rank 0, set 0); "
+                             f"OpenMP over the batch, {threads} threads = every usable CPU; acados-equivalent CPU restatement (oracle/), not acados"}
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one sqp_kernel launch (ncu --set full)
             tj = json.load(open(tpath))
             if tj.get("grid") == P:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        cfg = bench_config(S)  # identical in the reference arm's line
+        stats = {"resident_input_set_MB": input_bytes_resident / 1e6, "rotating_input_sets": NSETS,
+                 "success_fraction": frac_success, "mean_ipm_iterations_per_solve": mean_qp_iter, "mean_sqp_iterations_per_solve": mean_sqp_iter,
+                 "converged_fraction_1e-4": converged_fraction,
+                 "converged_fraction_note": f"of the solves feasible after 10 and after 40 RTI steps (first {n_cv} solves of set 0): share whose 10-step trajectory equals the 40-step one to 1e-4 relative",
+                 "control_step_latency_ms_P8_host_call": latency_ms,
+                 "e2e_call": "mpcgpu_solve_tmpc_host (one parameter block per control step; per-guess blocks + topology halfspaces built on the device)",
+                 "e2e_generic_call_solves_per_s": e2e_generic,
+                 "e2e_generic_call": "mpcgpu_solve_host (per-guess parameter blocks packed on the host)",
+                 "numa_node": numa_node}
+        fp64 = {"bound": "fp64", "achieved": achieved_gflops / 1e3, "peak": fp64_peak / 1e3, "unit": "TFLOP/s",
+                "frac": achieved_gflops / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                "flops_per_solve": fl, "flops_source": "profiles/r02_flops.json (scripts/count_flops.py: operation count of the kernel source, FMA = 2) x measured iteration counts",
+                "peak_source": "measured in this run (dependent-free DFMA chains, all SMs); MEASURED_PEAKS.json has no FP64 figure",
+                "kernel": "sqp_kernel", "kernel_ms": kernel_ms,
+                "note": "SURVEY.md 8d: arithmetic intensity ~110 FLOP/B, the FP64 pipe is the relevant roof; HBM is secondary (roofline_hbm)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(S), "l2": f"inputs larger than L2: rotating {NSETS} resident input sets of {input_bytes_resident / 1e6:.0f} MB",
-                       "solves_per_step_per_gpu": P, "success_fraction": frac_success, "mean_ipm_iterations_per_solve": mean_qp_iter,
-                       "control_step_latency_ms_P8_host_call": latency_ms,
-                       "e2e_call": "mpcgpu_solve_tmpc_host (one parameter block per control step; per-guess blocks + topology halfspaces built on the device)",
-                       "e2e_generic_call_solves_per_s": e2e_generic,
-                       "e2e_generic_call": "mpcgpu_solve_host (per-guess parameter blocks packed on the host)"},
-            "clocks": clocks,
+            "data": "synthetic", "config": cfg, "stats": stats, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SOLVE * P, "peak_source": peak_src, "kernel": "sqp_kernel", "kernel_ms": kernel_ms,
-                         "note": "latency/FP64-issue bound by design (SURVEY.md 8d); see fp64"},
-            "fp64": {"achieved": achieved_gflops, "peak": fp64_peak, "unit": "GFLOP/s", "frac": achieved_gflops / fp64_peak if fp64_peak > 0 else None,
-                     "flops_per_solve": fl, "peak_source": "measured in this run (dependent-free DFMA chains, all SMs)"},
+            "roofline": fp64,
+            "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                             "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SOLVE * P, "peak_source": peak_src,
+                             "kernel": "sqp_kernel", "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

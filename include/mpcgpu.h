@@ -27,6 +27,8 @@
 extern "C" {
 #endif
 
+typedef double mpcgpu_real;     /* every real number at this boundary is an IEEE-754 binary64 */
+
 #define MPCGPU_MAX_NZ 9          /* nu + nx upper bound (bicycle: 3 + 6)                       */
 #define MPCGPU_MAX_CON_MODULES 4 /* constraint blocks stacked in one problem                   */
 
@@ -130,6 +132,9 @@ int mpcgpu_problem_supported(const mpcgpu_problem_desc *desc);
  * (acados_solver_interface.cpp:17,33).  Device buffers are owned by the handle. */
 int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mpcgpu_handle *out);
 int mpcgpu_destroy(mpcgpu_handle h);
+
+/* The problem, device and capacity a handle was created with (any output may be NULL). */
+int mpcgpu_describe(mpcgpu_handle h, mpcgpu_problem_desc *desc, int *device, int *max_batch);
 
 /* Host-buffer path (what Solver::solve() uses): upload -> solve -> download, synchronous.
  *   xinit[P*nx], x0[P*(nu+nx)*(N+1)], params[P*npar*N]  -> xtraj[P*nx*(N+1)], utraj[P*nu*N], info[P]

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmpcgpu.so")
+DIST_LIB = os.path.join(LIB_DIR, "libmpcgpu_dist.so")  # multi-GPU best-trajectory reduction (links libnccl.so.2)
 SOURCES = ["mpcgpu.cu"]
 HEADERS = ["sqp_core.cuh", "stage_functions.cuh", "registry.cuh"]
 
@@ -52,5 +53,20 @@ def build(force=False, verbose=False, output=None, registry_header=None):
     return out
 
 
+def build_dist(force=False):
+    """libmpcgpu_dist.so: the NCCL best-trajectory reduction behind its own C ABI (include/mpcgpu_dist.h).  Links the
+    single-GPU library (found next to it through $ORIGIN) and libnccl.so.2."""
+    build()
+    src = os.path.join(CSRC, "mpcgpu_dist.cu")
+    deps = [src, os.path.join(ROOT, "include", "mpcgpu_dist.h"), os.path.join(ROOT, "include", "mpcgpu.h"), LIB]
+    if not force and os.path.exists(DIST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(DIST_LIB) for d in deps):
+        return DIST_LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-o", DIST_LIB, src, "-L" + LIB_DIR, "-lmpcgpu", "-lnccl",
+                                        "-Xlinker", "-rpath=$ORIGIN"]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return DIST_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_dist(force=True))

@@ -412,6 +412,14 @@ int mpcgpu_create(const mpcgpu_problem_desc *desc, int device, int max_batch, mp
     return MPCGPU_OK;
 }
 
+int mpcgpu_describe(mpcgpu_handle h, mpcgpu_problem_desc *desc, int *device, int *max_batch) {
+    if (!h) return MPCGPU_ERR_ARG;
+    if (desc) *desc = h->desc;
+    if (device) *device = h->device;
+    if (max_batch) *max_batch = h->max_batch;
+    return MPCGPU_OK;
+}
+
 int mpcgpu_destroy(mpcgpu_handle h) {
     if (!h) return MPCGPU_ERR_ARG;
     cudaSetDevice(h->device);

@@ -37,7 +37,9 @@
 
 // Development aid (-DMPC_PROFILE, scripts/profile_phases.py): thread 0 accumulates clock64() per phase
 // category in shared memory and the kernel writes the totals over the first doubles of utraj.
-#if defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
+#if defined(MPC_TICK)
+// supplied by the including translation unit (tests/emu/emu_count.cpp: FLOP counters per phase category)
+#elif defined(MPC_PROFILE) && defined(__CUDA_ARCH__)
 #define MPC_TICK(cat)                                                  \
     if (threadIdx.x == 0) {                                            \
         const long long now__ = clock64();                             \
@@ -1908,10 +1910,10 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         if (!(res_eq <= L.res_eq_fail) && exit_code == 1) exit_code = 4;  // acados_solver_interface.cpp:176-181
         if (!(pobj == pobj) || isinf(pobj)) exit_code = 4;               // a non-finite objective is never a success
         if (tid == 0) {
-            info->pobj = pobj;
-            info->res_eq = res_eq;
-            info->res_stat_qp = qp_res[0];
-            info->res_comp_qp = qp_res[1];
+            info->pobj = mpc_real(pobj);
+            info->res_eq = mpc_real(res_eq);
+            info->res_stat_qp = mpc_real(qp_res[0]);
+            info->res_comp_qp = mpc_real(qp_res[1]);
             info->exit_code = exit_code;
             info->qp_status = qp_status;
             info->sqp_iter = sqp_iter;
