@@ -504,30 +504,39 @@ def main():
         if rc != 0:
             raise RuntimeError(f"mpcgpu_solve_host: {rc}")
 
-    # The T-MPC++ call: one parameter block per control step (scene), the per-guess blocks and topology halfspaces are
-    # built on the device (mpcgpu_solve_tmpc_host) -- the call GuidanceConstraints::optimize makes.
+    # The T-MPC++ call from the compact scene description (mpcgpu_solve_tmpc_scene_host): per control step the host uploads
+    # what the modules' setParameters READ (stage-invariant weights / spline / disc parameters, obstacle predictions, radii)
+    # plus the guesses' warm starts; every per-stage parameter vector and the topology halfspaces are built on the device.
     t_in = []
     for hs in host_sets[:2]:
+        cs = scenes.compact_scene(spec, hs, S, GUESSES)
         d = {}
-        src = {"xinit": hs["xinit"].reshape(S, GUESSES, -1)[:, 0], "x0": hs["x0"],
-               "params": hs["params"].reshape(S, GUESSES, -1)[:, 0]}
+        src = {"xinit": cs["xinit"], "x0": hs["x0"], "base": cs["base_params"], "obstacles": cs["obstacles"], "radius": cs["obstacle_radius"]}
         for k, v in src.items():
             arr, ptr = pinned(v.shape)
             arr[...] = v
             d[k] = arr
             pins.append(ptr)
+        arr, ptr = pinned(cs["obstacle_flags"].shape, np.int32)
+        arr[...] = cs["obstacle_flags"]
+        d["flags"] = arr
+        pins.append(ptr)
+        d["risk"] = cs["risk"]
         t_in.append(d)
     guided = np.array([0] + [1] * (GUESSES - 1), dtype=np.int32)
+    n_obs_scene = int(t_in[0]["obstacles"].shape[1])
+    _ip = ctypes.POINTER(ctypes.c_int)
 
     def step_tmpc(j):
         hs = t_in[j % 2]
-        rc = lib.mpcgpu_solve_tmpc_host(solver.handle, S, GUESSES, hs["xinit"].ctypes.data_as(_dp), hs["x0"].ctypes.data_as(_dp),
-                                        hs["params"].ctypes.data_as(_dp), guided.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
-                                        float(scenes.ROBOT_RADIUS), h_xtraj.ctypes.data_as(_dp), h_utraj.ctypes.data_as(_dp),
-                                        ctypes.cast(h_info.ctypes.data, ctypes.POINTER(pb.SolveInfo)),
-                                        h_best.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+        rc = lib.mpcgpu_solve_tmpc_scene_host(solver.handle, S, GUESSES, hs["xinit"].ctypes.data_as(_dp), hs["x0"].ctypes.data_as(_dp),
+                                              hs["base"].ctypes.data_as(_dp), n_obs_scene, hs["obstacles"].ctypes.data_as(_dp),
+                                              hs["radius"].ctypes.data_as(_dp), hs["flags"].ctypes.data_as(_ip), float(hs["risk"]), 0, None,
+                                              guided.ctypes.data_as(_ip), float(scenes.ROBOT_RADIUS), h_xtraj.ctypes.data_as(_dp),
+                                              h_utraj.ctypes.data_as(_dp), ctypes.cast(h_info.ctypes.data, ctypes.POINTER(pb.SolveInfo)),
+                                              h_best.ctypes.data_as(_ip))
         if rc != 0:
-            raise RuntimeError(f"mpcgpu_solve_tmpc_host: {rc}")
+            raise RuntimeError(f"mpcgpu_solve_tmpc_scene_host: {rc}")
 
     def time_host(fn):
         for j in range(2):
@@ -545,7 +554,7 @@ def main():
     e2e_generic = time_host(step_host)
     e2e_value = time_host(step_tmpc)
     input_bytes_resident = sum(int(h_in[0][k].nbytes) for k in ("xinit", "x0", "params"))
-    h2d = sum(int(t_in[0][k].nbytes) for k in ("xinit", "x0", "params")) + int(guided.nbytes)
+    h2d = sum(int(t_in[0][k].nbytes) for k in ("xinit", "x0", "base", "obstacles", "radius", "flags")) + int(guided.nbytes)
     d2h = int(h_xtraj.nbytes + h_utraj.nbytes + h_info.nbytes + h_best.nbytes)
     for ptr in pins:
         lib.mpcgpu_host_free(ptr)
@@ -587,7 +596,7 @@ def main():
                  "converged_fraction_1e-4": converged_fraction,
                  "converged_fraction_note": f"of the solves feasible after 10 and after 40 RTI steps (first {n_cv} solves of set 0): share whose 10-step trajectory equals the 40-step one to 1e-4 relative",
                  "control_step_latency_ms_P8_host_call": latency_ms,
-                 "e2e_call": "mpcgpu_solve_tmpc_host (one parameter block per control step; per-guess blocks + topology halfspaces built on the device)",
+                 "e2e_call": "mpcgpu_solve_tmpc_scene_host (compact scene per control step: stage-invariant parameters + obstacle predictions + warm starts; every per-stage parameter vector and the topology halfspaces are built on the device)",
                  "e2e_generic_call_solves_per_s": e2e_generic,
                  "e2e_generic_call": "mpcgpu_solve_host (per-guess parameter blocks packed on the host)",
                  "numa_node": numa_node}

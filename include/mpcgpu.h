@@ -173,6 +173,33 @@ int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, c
                            const double *scene_params, const int *guided, double robot_radius, double *xtraj,
                            double *utraj, mpcgpu_info *info, int *best);
 
+/* T-MPC++ control steps from a COMPACT scene description: the whole per-stage parameter vector of every guess is built on
+ * the device.  Replaces, for S control steps x G guesses, the host-side stage-by-stage writes of MPCBaseModule /
+ * Contouring / EllipsoidConstraints / GaussianConstraints / DecompConstraints ::setParameters (mpc_base.cpp:23-35,
+ * contouring.cpp:94-124, ellipsoid_constraints.cpp:34-90, gaussian_constraints.cpp:31-79, decomp_constraints.cpp:90-114,
+ * 150-189) and LinearizedConstraints::update / projectToSafety / setParameters (linearized_constraints.cpp:49-189); the
+ * host uploads what those functions READ (RealTimeData / ModuleData), not what they write:
+ *   base_params[S*npar]      the stage-invariant part of one stage's parameter vector: weights, spline coefficients of the
+ *                            segment window, ego disc radius / offset (the constraint blocks' slots are ignored)
+ *   obstacles[S*n_obs*N*5]   prediction step j = 0..N-1 of obstacle o: x, y, psi, major, minor; step j feeds stage j + 1,
+ *                            stage 0 gets the reference's far-away dummies
+ *   obstacle_radius[S*n_obs], obstacle_flags[S*n_obs] (bit 0: Gaussian prediction, else deterministic: major = minor = 0,
+ *                            chi = 1; bit 1: static obstacle: Gaussian block uses 0.001 for its axes), risk (chi =
+ *                            ExponentialQuantile(0.5, 1 - risk) for the ellipsoid block, `risk` for the Gaussian block)
+ *   halfspaces[S*N*n_halfspaces*3] or NULL   rows (a1, a2, b) of the DECOMP block of stage k (polyhedron k - 1), the
+ *                            first zero / NaN normal ends a stage's list, dummies (1, 0, x0 + 100) behind it
+ *   xinit, x0, guided, robot_radius, outputs: as mpcgpu_solve_tmpc_host.
+ * Every block kind except SCENARIO (built by the external scenario_module) is supported.  Per control step the upload is
+ * npar + 5 N n_obs + 2 n_obs (+ 3 N n_halfspaces) doubles instead of N * npar. */
+int mpcgpu_solve_tmpc_scene_host(mpcgpu_handle h, int S, int G, const double *xinit, const double *x0, const double *base_params,
+                                 int n_obs, const double *obstacles, const double *obstacle_radius, const int *obstacle_flags,
+                                 double risk, int n_halfspaces, const double *halfspaces, const int *guided, double robot_radius,
+                                 double *xtraj, double *utraj, mpcgpu_info *info, int *best);
+
+/* Debug / parity: the parameter blocks the device-side packing of the last T-MPC call left in HBM, in the reference's
+ * stage-major layout params[P][N][npar]. */
+int mpcgpu_get_packed_params(mpcgpu_handle h, int P, double *params);
+
 /* Persistent NLP multipliers ("stateful" solver slots).  In the reference every LocalPlanner owns a Solver whose
  * acados memory survives `*local_solver = *_solver` (operator= copies parameters only,
  * acados_solver_interface.cpp:67-77): the multipliers of its previous solve enter the first exact Hessian of the next

@@ -20,7 +20,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 # every symbol include/mpcgpu.h declares
 EXPORTED_SYMBOLS = [
     "mpcgpu_version", "mpcgpu_strerror", "mpcgpu_device_count", "mpcgpu_problem_supported", "mpcgpu_create", "mpcgpu_destroy", "mpcgpu_describe",
-    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_set_group", "mpcgpu_set_timeout",
+    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_solve_tmpc_scene_host", "mpcgpu_get_packed_params", "mpcgpu_set_group", "mpcgpu_set_timeout",
     "mpcgpu_set_stateful", "mpcgpu_state_size", "mpcgpu_reset_state", "mpcgpu_get_state", "mpcgpu_set_state", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
     "mpcgpu_set_timing", "mpcgpu_kernel_ms", "mpcgpu_eval_stage", "mpcgpu_measure_fp64_gflops",
 ]
@@ -51,6 +51,9 @@ def load_library(path: str | None = None):
     lib.mpcgpu_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 8
     lib.mpcgpu_solve_tmpc_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, _ip, ctypes.c_double, _dp, _dp,
                                            ctypes.POINTER(SolveInfo), _ip]
+    lib.mpcgpu_solve_tmpc_scene_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _dp, _dp, _ip, ctypes.c_double,
+                                                 ctypes.c_int, _dp, _ip, ctypes.c_double, _dp, _dp, ctypes.POINTER(SolveInfo), _ip]
+    lib.mpcgpu_get_packed_params.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp]
     lib.mpcgpu_set_group.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.mpcgpu_set_stateful.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.mpcgpu_set_timeout.argtypes = [ctypes.c_void_p, ctypes.c_double]
@@ -183,6 +186,43 @@ class BatchSolver:
                                                float(robot_radius), _p(xtraj), _p(utraj), info, best.ctypes.data_as(_ip)),
                "mpcgpu_solve_tmpc_host")
         return xtraj, utraj, infos_to_dicts(info), best
+
+    def solve_tmpc_scene(self, xinit, x0, base_params, obstacles, obstacle_radius, obstacle_flags, guided, risk=0.05, halfspaces=None,
+                         robot_radius=0.325):
+        """S control steps x G guesses from the compact scene description (mpcgpu_solve_tmpc_scene_host).
+        obstacles [S, n_obs, N, 5] (x, y, psi, major, minor per prediction step), halfspaces [S, N, n_hs, 3] or None."""
+        s = self.spec
+        xinit = np.ascontiguousarray(xinit, float).reshape(-1, s.nx)
+        S = xinit.shape[0]
+        guided = np.ascontiguousarray(guided, np.int32)
+        G = len(guided)
+        P = S * G
+        x0 = np.ascontiguousarray(x0, float).reshape(P, s.nz * (s.N + 1))
+        base_params = np.ascontiguousarray(base_params, float).reshape(S, s.npar)
+        obstacles = np.ascontiguousarray(obstacles, float)
+        n_obs = obstacles.shape[1] if obstacles.size else 0
+        assert obstacles.size == 0 or obstacles.shape == (S, n_obs, s.N, 5)
+        obstacle_radius = np.ascontiguousarray(obstacle_radius, float).reshape(S, n_obs)
+        obstacle_flags = np.ascontiguousarray(obstacle_flags, np.int32).reshape(S, n_obs)
+        n_hs = 0
+        if halfspaces is not None:
+            halfspaces = np.ascontiguousarray(halfspaces, float)
+            n_hs = halfspaces.shape[2]
+            assert halfspaces.shape == (S, s.N, n_hs, 3)
+        xtraj, utraj = np.empty((P, s.N + 1, s.nx)), np.empty((P, s.N, s.nu))
+        info = (SolveInfo * P)()
+        best = np.full(S, -1, dtype=np.int32)
+        _check(self.lib.mpcgpu_solve_tmpc_scene_host(self.handle, S, G, _p(xinit), _p(x0), _p(base_params), n_obs, _p(obstacles), _p(obstacle_radius),
+                                                     obstacle_flags.ctypes.data_as(_ip), float(risk), n_hs, _p(halfspaces),
+                                                     guided.ctypes.data_as(_ip), float(robot_radius), _p(xtraj), _p(utraj), info,
+                                                     best.ctypes.data_as(_ip)), "mpcgpu_solve_tmpc_scene_host")
+        return xtraj, utraj, infos_to_dicts(info), best
+
+    def packed_params(self, P):
+        """Parameter blocks of the last device-packed call, reference layout [P, N * npar] (debug / parity)."""
+        out = np.empty((P, self.spec.N * self.spec.npar))
+        _check(self.lib.mpcgpu_get_packed_params(self.handle, int(P), _p(out)), "mpcgpu_get_packed_params")
+        return out
 
     # ---- device-buffer path (raw pointers, e.g. torch tensors' data_ptr()) ----
     def solve_device(self, P, d_xinit, d_x0, d_params, d_xtraj, d_utraj, d_info, d_best=None, stream=None):

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 
+#include "projection.cuh"
 #include "registry.cuh"
 
 using namespace mpcgpu;
@@ -94,16 +95,14 @@ __global__ void pack_tmpc_kernel(const double *__restrict__ scene_params, const 
         if (build) {
             px = x0[((size_t)p * (N + 1) + k) * nz + nu];
             py = x0[((size_t)p * (N + 1) + k) * nz + nu + 1];
-            for (int sweep = 0; sweep < 3; sweep++)  // projectToSafety: at most 3 sweeps (stand-in for Douglas-Rachford)
-                for (int o = 0; o < n_obs; o++) {
-                    const double ox = sp[k * npar + obs0 + obs_stride * o], oy = sp[k * npar + obs0 + obs_stride * o + 1];
-                    double dx = px - ox, dy = py - oy, dist = sqrt(dx * dx + dy * dy);
-                    if (dist < R) {
-                        if (dist < 1e-9) { dx = 1.0; dy = 0.0; dist = 1.0; }
-                        px = ox + dx / dist * R;
-                        py = oy + dy / dist * R;
-                    }
-                }
+            // projectToSafety (linearized_constraints.cpp:130-148): at most 3 Douglas-Rachford sweeps over the obstacles,
+            // anchor = obstacle 0 of this stage
+            if (n_obs > 0) {
+                const double ax = sp[k * npar + obs0], ay = sp[k * npar + obs0 + 1];
+                for (int sweep = 0; sweep < 3; sweep++)
+                    for (int o = 0; o < n_obs; o++)
+                        douglas_rachford_projection(px, py, sp[k * npar + obs0 + obs_stride * o], sp[k * npar + obs0 + obs_stride * o + 1], ax, ay, R);
+            }
         }
         for (int j = 0; j < n_lin; j++) {
             double a1 = 1.0, a2 = 0.0, b = x_init + 100.0;  // dummies (linearized_constraints.cpp:53,155-166,181-187)
@@ -125,6 +124,114 @@ __global__ void pack_tmpc_kernel(const double *__restrict__ scene_params, const 
             ptp[(lin0 + 3 * j) * PT + k] = a1;
             ptp[(lin0 + 3 * j + 1) * PT + k] = a2;
             ptp[(lin0 + 3 * j + 2) * PT + k] = b;
+        }
+    }
+}
+
+// T-MPC++ from a COMPACT scene description: per (control step s, guess g) the whole transposed parameter block is built on
+// the device -- what MPCBaseModule / Contouring / EllipsoidConstraints / GaussianConstraints / DecompConstraints ::
+// setParameters and LinearizedConstraints::update + setParameters write stage by stage on the host in the reference
+// (mpc_base.cpp:23-35, contouring.cpp:94-124, ellipsoid_constraints.cpp:34-90, gaussian_constraints.cpp:31-79,
+// decomp_constraints.cpp:90-114,150-189, linearized_constraints.cpp:49-189).  See mpcgpu_solve_tmpc_scene_host.
+struct SceneBlocks {
+    int n_mod, kind[3], p0[3], count[3];
+};
+__global__ void pack_scene_kernel(const double *__restrict__ base, const double *__restrict__ obstacles, const double *__restrict__ radius,
+                                  const int *__restrict__ flags, const double *__restrict__ halfspaces, int n_hs, double risk,
+                                  const double *__restrict__ xinit_scene, const double *__restrict__ x0, const int *__restrict__ guided,
+                                  double *__restrict__ pt, double *__restrict__ xinit_out, int S, int G, int N, int npar, int nx, int nu,
+                                  SceneBlocks B, int n_obs, double robot_radius, long long *t_call) {
+    stamp_call_start(t_call);
+    const int p = blockIdx.x, s = p / G, g = p - s * G;
+    if (s >= S) return;
+    const int PT = pt_stride(N), nz = nx + nu;
+    double *ptp = pt + (size_t)p * npar * PT;
+    const double *bs = base + (size_t)s * npar;
+    for (int idx = threadIdx.x; idx < N * npar; idx += blockDim.x) {
+        const int i = idx / N, k = idx - i * N;
+        ptp[i * PT + k] = bs[i];  // stage-invariant part (weights, spline, ego disc): the same at every stage
+    }
+    if (threadIdx.x < nx) xinit_out[(size_t)p * nx + threadIdx.x] = xinit_scene[(size_t)s * nx + threadIdx.x];
+    __syncthreads();
+    const double x_init = xinit_scene[(size_t)s * nx], y_init = xinit_scene[(size_t)s * nx + 1];
+    const double *ob = obstacles + (size_t)s * n_obs * N * 5;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        for (int m = 0; m < B.n_mod; m++) {
+            const int kind = B.kind[m], p0 = B.p0[m], cnt = B.count[m];
+            if (kind == MPCGPU_CON_ELLIPSOID) {
+                for (int o = 0; o < cnt; o++) {
+                    double v[7] = {x_init + 50.0, y_init + 50.0, 0.0, 0.0, 0.0, 1.0, 0.1};  // stage 0 dummies (:42-55)
+                    if (k >= 1 && o < n_obs) {
+                        const double *st = ob + ((size_t)o * N + (k - 1)) * 5;  // prediction step k - 1 feeds stage k (:67-70)
+                        const bool gauss = (flags[(size_t)s * n_obs + o] & 1) != 0;
+                        v[0] = st[0]; v[1] = st[1]; v[2] = st[2];
+                        v[3] = gauss ? st[3] : 0.0;
+                        v[4] = gauss ? st[4] : 0.0;
+                        v[5] = gauss ? -log(risk) / 0.5 : 1.0;  // RosTools::ExponentialQuantile(0.5, 1 - risk) (:80)
+                        v[6] = radius[(size_t)s * n_obs + o];
+                    }
+                    for (int c = 0; c < 7; c++) ptp[(p0 + 7 * o + c) * PT + k] = v[c];
+                }
+            } else if (kind == MPCGPU_CON_GAUSSIAN) {
+                for (int o = 0; o < cnt; o++) {
+                    double v[6] = {x_init + 100.0, y_init + 100.0, 0.1, 0.1, 0.05, 0.1};  // (:39-52)
+                    if (k >= 1 && o < n_obs && (flags[(size_t)s * n_obs + o] & 1)) {
+                        const double *st = ob + ((size_t)o * N + (k - 1)) * 5;
+                        const bool is_static = (flags[(size_t)s * n_obs + o] & 2) != 0;  // static obstacles: no uncertainty (:72-73)
+                        v[0] = st[0]; v[1] = st[1];
+                        v[2] = is_static ? 0.001 : st[3];
+                        v[3] = is_static ? 0.001 : st[4];
+                        v[4] = risk;
+                        v[5] = radius[(size_t)s * n_obs + o];
+                    }
+                    for (int c = 0; c < 6; c++) ptp[(p0 + 6 * o + c) * PT + k] = v[c];
+                }
+            } else if (kind == MPCGPU_CON_LINEAR) {
+                const bool build = (guided[g] != 0) && (k >= 1);
+                double px = 0.0, py = 0.0;
+                const double R = 1e-3 + robot_radius;  // topology mode (linearized_constraints.cpp:101)
+                if (build) {
+                    px = x0[((size_t)p * (N + 1) + k) * nz + nu];
+                    py = x0[((size_t)p * (N + 1) + k) * nz + nu + 1];
+                    if (n_obs > 0) {
+                        const double *a0 = ob + (size_t)(k - 1) * 5;
+                        for (int sweep = 0; sweep < 3; sweep++)
+                            for (int o = 0; o < n_obs; o++) {
+                                const double *st = ob + ((size_t)o * N + (k - 1)) * 5;
+                                douglas_rachford_projection(px, py, st[0], st[1], a0[0], a0[1], R);
+                            }
+                    }
+                }
+                for (int j = 0; j < cnt; j++) {
+                    double a1 = 1.0, a2 = 0.0, b = x_init + 100.0;
+                    if (build && j < n_obs) {
+                        const double *st = ob + ((size_t)j * N + (k - 1)) * 5;
+                        double dx = st[0] - px, dy = st[1] - py, dist = sqrt(dx * dx + dy * dy);
+                        if (dist < 1e-9) { dx = 1.0; dy = 0.0; dist = 1.0; }
+                        a1 = dx / dist;
+                        a2 = dy / dist;
+                        b = a1 * st[0] + a2 * st[1] - R;
+                    }
+                    ptp[(p0 + 3 * j) * PT + k] = a1;
+                    ptp[(p0 + 3 * j + 1) * PT + k] = a2;
+                    ptp[(p0 + 3 * j + 2) * PT + k] = b;
+                }
+            } else {  // DECOMP: rows from outside up to the first zero / NaN normal, dummies behind (decomp_constraints.cpp:90-114)
+                bool valid = (k >= 1) && halfspaces != nullptr;
+                for (int j = 0; j < cnt; j++) {
+                    double a1 = 1.0, a2 = 0.0, b = x_init + 100.0;
+                    if (valid && j < n_hs) {
+                        const double *hs = halfspaces + (((size_t)s * N + k) * n_hs + j) * 3;
+                        if (sqrt(hs[0] * hs[0] + hs[1] * hs[1]) < 1e-3 || hs[0] != hs[0]) valid = false;
+                        else { a1 = hs[0]; a2 = hs[1]; b = hs[2]; }
+                    } else {
+                        valid = false;
+                    }
+                    ptp[(p0 + 3 * j) * PT + k] = a1;
+                    ptp[(p0 + 3 * j + 1) * PT + k] = a2;
+                    ptp[(p0 + 3 * j + 2) * PT + k] = b;
+                }
+            }
         }
     }
 }
@@ -317,6 +424,9 @@ struct mpcgpu_solver {
     size_t n_state;
     int *d_guided;             // T-MPC guided flags (lazy)
     double *d_xinit_scene;     // T-MPC per-control-step initial states (lazy)
+    double *d_scene;           // compact scene tensors of the scene path (lazy): base | obstacles | radius | halfspaces
+    int *d_scene_flags;
+    size_t scene_doubles;
     long long launches;
     int group;  // solves per selection group (0 = the whole batch)
     int timing;
@@ -436,6 +546,8 @@ int mpcgpu_destroy(mpcgpu_handle h) {
     cudaFree(h->d_state);
     cudaFree(h->d_guided);
     cudaFree(h->d_xinit_scene);
+    cudaFree(h->d_scene);
+    cudaFree(h->d_scene_flags);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -617,6 +729,120 @@ int mpcgpu_solve_tmpc_host(mpcgpu_handle h, int S, int G, const double *xinit, c
         h->ms_acc += ms;
         h->ms_n += 1;
     }
+    return MPCGPU_OK;
+}
+
+int mpcgpu_solve_tmpc_scene_host(mpcgpu_handle h, int S, int G, const double *xinit, const double *x0, const double *base_params,
+                                 int n_obs, const double *obstacles, const double *obstacle_radius, const int *obstacle_flags, double risk,
+                                 int n_halfspaces, const double *halfspaces, const int *guided, double robot_radius, double *xtraj,
+                                 double *utraj, mpcgpu_info *info, int *best) {
+    if (!h || S <= 0 || G <= 0 || G > 1024 || !xinit || !x0 || !base_params || !guided || !xtraj || !utraj || !info || n_obs < 0 || n_halfspaces < 0) return MPCGPU_ERR_ARG;
+    if (n_obs > 0 && (!obstacles || !obstacle_radius || !obstacle_flags)) return MPCGPU_ERR_ARG;
+    if (!(risk > 0.0 && risk < 1.0)) return MPCGPU_ERR_ARG;
+    const int P = S * G;
+    if (P > h->max_batch) return MPCGPU_ERR_BATCH;
+    const mpcgpu_problem_desc &d = h->desc;
+    SceneBlocks B;
+    B.n_mod = d.n_con_modules;
+    for (int m = 0; m < 3; m++) {
+        B.kind[m] = (m < d.n_con_modules) ? d.con_kind[m] : 0;
+        B.p0[m] = (m < d.n_con_modules) ? d.con_param[m] : 0;
+        B.count[m] = (m < d.n_con_modules) ? d.con_count[m] : 0;
+        if (m < d.n_con_modules && d.con_kind[m] == MPCGPU_CON_SCENARIO) return MPCGPU_ERR_UNSUPPORTED;  // built by the external scenario_module
+        if (m < d.n_con_modules && (d.con_kind[m] == MPCGPU_CON_ELLIPSOID || d.con_kind[m] == MPCGPU_CON_GAUSSIAN) && n_obs > d.con_count[m]) return MPCGPU_ERR_ARG;
+    }
+    const int N = d.N, npar = d.npar;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->d_guided) {
+        CUDA_TRY(cudaMalloc(&h->d_guided, 1024 * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_xinit_scene, (size_t)h->max_batch * h->n_xinit * sizeof(double)));
+    }
+    // staging of the compact scene: [base S*npar | obstacles S*n_obs*N*5 | radius S*n_obs | halfspaces S*N*n_hs*3]
+    const size_t n_base = (size_t)S * npar, n_ob = (size_t)S * n_obs * N * 5, n_rad = (size_t)S * n_obs;
+    const size_t n_hs = halfspaces ? (size_t)S * N * n_halfspaces * 3 : 0, need = n_base + n_ob + n_rad + n_hs;
+    if (need > h->scene_doubles) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream2));
+        cudaFree(h->d_scene);
+        cudaFree(h->d_scene_flags);
+        h->d_scene = nullptr;
+        h->d_scene_flags = nullptr;
+        h->scene_doubles = 0;
+        CUDA_TRY(cudaMalloc(&h->d_scene, need * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->d_scene_flags, ((size_t)h->max_batch * 64 + 64) * sizeof(int)));
+        h->scene_doubles = need;
+    }
+    if ((size_t)S * n_obs > (size_t)h->max_batch * 64 + 64) return MPCGPU_ERR_ARG;
+    double *d_base = h->d_scene, *d_ob = d_base + n_base, *d_rad = d_ob + n_ob, *d_hs = d_rad + n_rad;
+    int n_chunks = (P >= 2048) ? 4 : 1;
+    int sc_chunk = (S + n_chunks - 1) / n_chunks;
+    n_chunks = (S + sc_chunk - 1) / sc_chunk;
+    CUDA_TRY(cudaMemcpyAsync(h->d_guided, guided, (size_t)G * sizeof(int), cudaMemcpyHostToDevice, h->stream_in));
+    for (int c = 0; c < n_chunks; c++) {
+        const size_t s0 = (size_t)c * sc_chunk, ns = (s0 + sc_chunk <= (size_t)S) ? sc_chunk : S - s0, p0 = s0 * G, np = ns * G;
+        CUDA_TRY(cudaMemcpyAsync(d_base + s0 * npar, base_params + s0 * npar, ns * npar * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        if (n_obs > 0) {
+            CUDA_TRY(cudaMemcpyAsync(d_ob + s0 * n_obs * N * 5, obstacles + s0 * n_obs * N * 5, ns * n_obs * N * 5 * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+            CUDA_TRY(cudaMemcpyAsync(d_rad + s0 * n_obs, obstacle_radius + s0 * n_obs, ns * n_obs * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+            CUDA_TRY(cudaMemcpyAsync(h->d_scene_flags + s0 * n_obs, obstacle_flags + s0 * n_obs, ns * n_obs * sizeof(int), cudaMemcpyHostToDevice, h->stream_in));
+        }
+        if (n_hs) CUDA_TRY(cudaMemcpyAsync(d_hs + s0 * N * n_halfspaces * 3, halfspaces + s0 * N * n_halfspaces * 3, ns * N * n_halfspaces * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaMemcpyAsync(h->d_x0 + p0 * h->n_x0, x0 + p0 * h->n_x0, np * h->n_x0 * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaMemcpyAsync(h->d_xinit_scene + s0 * h->n_xinit, xinit + s0 * h->n_xinit, ns * h->n_xinit * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[c], h->stream_in));
+    }
+    for (int c = 0; c < n_chunks; c++) {
+        const size_t s0 = (size_t)c * sc_chunk, ns = (s0 + sc_chunk <= (size_t)S) ? sc_chunk : S - s0, p0 = s0 * G, np = ns * G;
+        cudaStream_t sc = (c & 1) ? h->stream2 : h->stream;
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_in[c], 0));
+        long long *t_call = (h->layout.timeout_s > 0.0) ? h->d_t_call + c : nullptr;
+        pack_scene_kernel<<<(unsigned)np, 128, 0, sc>>>(d_base + s0 * npar, d_ob + s0 * n_obs * N * 5, d_rad + s0 * n_obs, h->d_scene_flags + s0 * n_obs,
+                                                        n_hs ? d_hs + s0 * N * n_halfspaces * 3 : nullptr, n_halfspaces, risk, h->d_xinit_scene + s0 * h->n_xinit,
+                                                        h->d_x0 + p0 * h->n_x0, h->d_guided, h->d_pt + p0 * (size_t)npar * pt_stride(N), h->d_xinit + p0 * h->n_xinit,
+                                                        (int)ns, G, N, npar, d.nx, d.nu, B, n_obs, robot_radius, t_call);
+        const bool timed = h->timing != 0 && n_chunks == 1;
+        if (timed) cudaEventRecord(h->ev0, sc);
+        Layout L = h->layout;
+        L.t_call = t_call;
+        h->kt->launch_sqp(L, (int)np, h->d_xinit + p0 * h->n_xinit, h->d_x0 + p0 * h->n_x0, h->d_pt + p0 * (size_t)npar * pt_stride(N),
+                          h->d_xtraj + p0 * h->n_xtraj, h->d_utraj + p0 * h->n_utraj, h->d_info + p0, h->d_sm_slots,
+                          h->d_state ? h->d_state + p0 * h->n_state : nullptr, h->kt->smem_bytes, sc);
+        if (timed) cudaEventRecord(h->ev1, sc);
+        select_best_kernel<<<(unsigned)((ns + 3) / 4), 128, 0, sc>>>(h->d_info + p0, (int)np, G, (int)ns, h->d_best + s0);
+        h->launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(h->ev_cmp[c], sc));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream_out, h->ev_cmp[c], 0));
+        CUDA_TRY(cudaMemcpyAsync(xtraj + p0 * h->n_xtraj, h->d_xtraj + p0 * h->n_xtraj, np * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
+        CUDA_TRY(cudaMemcpyAsync(utraj + p0 * h->n_utraj, h->d_utraj + p0 * h->n_utraj, np * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
+        CUDA_TRY(cudaMemcpyAsync(info + p0, h->d_info + p0, np * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, h->stream_out));
+        if (best) CUDA_TRY(cudaMemcpyAsync(best + s0, h->d_best + s0, ns * sizeof(int), cudaMemcpyDeviceToHost, h->stream_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream_out));
+    if (h->timing && n_chunks == 1) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->ms_acc += ms;
+        h->ms_n += 1;
+    }
+    return MPCGPU_OK;
+}
+
+// Debug / parity: the parameter blocks the device-side packing of the last scene call left in HBM, back in the reference's
+// stage-major layout params[P][N][npar].
+int mpcgpu_get_packed_params(mpcgpu_handle h, int P, double *params) {
+    if (!h || P <= 0 || P > h->max_batch || !params) return MPCGPU_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int N = h->desc.N, npar = h->desc.npar, PT = pt_stride(N);
+    double *tmp = (double *)malloc((size_t)P * npar * PT * sizeof(double));
+    if (!tmp) return MPCGPU_ERR_ALLOC;
+    cudaError_t e = cudaMemcpy(tmp, h->d_pt, (size_t)P * npar * PT * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        for (int p = 0; p < P; p++)
+            for (int k = 0; k < N; k++)
+                for (int i = 0; i < npar; i++) params[((size_t)p * N + k) * npar + i] = tmp[((size_t)p * npar + i) * PT + k];
+    free(tmp);
+    CUDA_TRY(e);
     return MPCGPU_OK;
 }
 

@@ -1840,7 +1840,9 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
             const int it = (tid & 31) * NW + (tid >> 5);
             if ((tid & 31) < (NI + NW - 1) / NW && it < NI) {
                 mirror_stage<CFG>(L, sm + (it >> 1) * S::STRIDE, it & 1);
-                if (sm[(it >> 1) * S::STRIDE + S::DZN] == 2.0) need_general |= 1;
+                // only the thread that may have written the flag reads it back (the part-1 thread of the same stage would
+                // race with that write: compute-sanitizer racecheck, profiles/r02_sanitizer.md)
+                if ((it & 1) == 0 && sm[(it >> 1) * S::STRIDE + S::DZN] == 2.0) need_general |= 1;
             }
         }
         MPC_PHASE_END_OR(need_general)
@@ -1877,6 +1879,11 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         if (W[S::W_TMO] != 0.0) break;  // out of time (:112-116)
     }
 
+    // A QP failure leaves the loop straight after the residual check of ipm_solve: every thread has read the reduction
+    // slots there, and the phase below writes them again -- one barrier in between (racecheck, profiles/r02_sanitizer.md)
+#if defined(__CUDACC__)
+    __syncthreads();
+#endif
     // completeOneIteration (acados_solver_interface.cpp:162-204): cost, trajectories, res_eq
     MPC_PHASE
     {

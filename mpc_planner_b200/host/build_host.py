@@ -36,16 +36,17 @@ def build_modules_test(name="cfg2", out_dir=None):
     return exe
 
 
-def build_planner_test(name="cfg2", out_dir=None):
+def build_planner_test(name="cfg2", out_dir=None, nvtx=False):
     """Planner::solveMPC (host/src/planner.cpp) + the closed-loop driver."""
     spec = pb.CONFIGS[name]()
     out_dir = out_dir or os.path.join(HERE, "generated", name)
     generate_solver(spec, out_dir)
-    exe = os.path.join(out_dir, "test_planner")
+    exe = os.path.join(out_dir, "test_planner_nvtx" if nvtx else "test_planner")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [cxx, "-O2", "-std=c++17", "-I" + out_dir, "-I" + os.path.join(HERE, "include"), "-I" + os.path.join(libbuild.ROOT, "include"),
+    extra = ["-DMPC_PLANNER_NVTX", "-I/usr/local/cuda/include"] if nvtx else []  # PROFILE_SCOPE -> NVTX ranges (header-only nvtx3 + libdl)
+    cmd = [cxx, "-O2", "-std=c++17"] + extra + ["-I" + out_dir, "-I" + os.path.join(HERE, "include"), "-I" + os.path.join(libbuild.ROOT, "include"),
            os.path.join(HERE, "src", "cuda_solver_interface.cpp"), os.path.join(HERE, "src", "modules.cpp"), os.path.join(HERE, "src", "planner.cpp"),
-           os.path.join(HERE, "test", "test_planner.cpp"), "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-o", exe]
+           os.path.join(HERE, "test", "test_planner.cpp"), "-L" + libbuild.LIB_DIR, "-lmpcgpu", "-Wl,-rpath," + libbuild.LIB_DIR, "-ldl", "-o", exe]
     subprocess.check_call(cmd)
     return exe
 

@@ -2,6 +2,10 @@
 #include <mpc_planner_modules/modules.h>
 
 #include <algorithm>
+
+#include <mpc_planner_util/profiling.h>
+
+#include "../../csrc/projection.cuh"
 #include <cmath>
 
 namespace MPCPlanner {
@@ -235,18 +239,14 @@ void LinearizedConstraints::update(State &state, const RealTimeData &data, Modul
 }
 void LinearizedConstraints::projectToSafety(const std::vector<DynamicObstacle> &copied_obstacles, int k, Vec2 &pos) {  // :130-148
     if (copied_obstacles.empty()) return;
-    // The reference calls RosTools::DouglasRachford::douglasRachfordProjection (ros_tools, un-vendored).  Stand-in with
-    // the same contract (at most 3 sweeps; the point ends up outside every obstacle disc): radial projection.
+    // RosTools::DouglasRachford::douglasRachfordProjection (ros_tools, un-vendored): restated in csrc/projection.cuh, the
+    // one definition host and device share.  At most 3 sweeps, anchor = obstacle 0 of the stage (:136-146).
+    const Vec2 &anchor = copied_obstacles[0].prediction.modes[0][k - 1].position;
     for (int iterate = 0; iterate < 3; iterate++)
         for (const auto &obstacle : copied_obstacles) {
             const double r = (_use_guidance ? 1e-3 : obstacle.radius) + CONFIG().robot_radius;
             const Vec2 &op = obstacle.prediction.modes[0][k - 1].position;
-            double dx = pos[0] - op[0], dy = pos[1] - op[1];
-            double dist = std::sqrt(dx * dx + dy * dy);
-            if (dist < r) {
-                if (dist < 1e-9) { dx = 1.0; dy = 0.0; dist = 1.0; }
-                pos = {op[0] + dx / dist * r, op[1] + dy / dist * r};
-            }
+            mpcgpu::douglas_rachford_projection(pos[0], pos[1], op[0], op[1], anchor[0], anchor[1], r);
         }
 }
 void LinearizedConstraints::setParameters(const RealTimeData &data, const ModuleData &, int k) {  // :150-189
@@ -427,13 +427,18 @@ std::vector<typename GuidanceConstraintsT<SC>::LocalPlanner *> GuidanceConstrain
 
 template <class SC>
 int GuidanceConstraintsT<SC>::optimize(State &state, const RealTimeData &data, ModuleData &module_data) {  // :264-388
+    PROFILE_FUNCTION();  // :266
     if (!CONFIG().use_tmpcpp && _guidance.empty()) return 0;
     std::vector<LocalPlanner *> active = prepare(state, data, module_data);
     std::vector<Solver *> batch;
     for (LocalPlanner *p : active) batch.push_back(p->local_solver.get());
     // ... and the P solves as ONE batched launch
     std::vector<int> exit_codes;
-    Solver::solveBatch(batch, exit_codes);
+    {
+        PROFILE_SCOPE("Guidance Constraints: Parallel Optimization");  // :282 (here: one batched launch)
+        Solver::solveBatch(batch, exit_codes);
+    }
+    PROFILE_SCOPE("Decision");  // :366
     for (size_t i = 0; i < active.size(); i++) {
         LocalPlanner &planner = *active[i];
         planner.result.exit_code = exit_codes[i];

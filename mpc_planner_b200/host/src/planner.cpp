@@ -1,5 +1,6 @@
 // planner.cpp -- see include/mpc_planner/planner.h.  Reference: mpc_planner/src/planner.cpp.
 #include <mpc_planner/planner.h>
+#include <mpc_planner_util/profiling.h>
 
 namespace MPCPlanner {
 
@@ -37,6 +38,7 @@ int Planner::bestPlannerIndex() const {
 }
 
 PlannerOutput Planner::solveMPC(State &state, RealTimeData &data) {  // :37-158
+    PROFILE_SCOPE("Planning");  // :69
     const bool was_feasible = _output.success;
     _output = PlannerOutput(_solver->dt, _solver->N);
     _module_data = ModuleData();  // reset module data (:43); the path arrives through onDataReceived in the reference
@@ -58,10 +60,16 @@ PlannerOutput Planner::solveMPC(State &state, RealTimeData &data) {  // :37-158
         _solver->initializeWithBraking(state);
     _solver->setXinit(state);  // :88
 
-    for (auto &module : _modules) module->update(state, data, _module_data);  // :95-96
+    {
+        PROFILE_SCOPE("Update");  // :93
+        for (auto &module : _modules) module->update(state, data, _module_data);  // :95-96
+    }
     _solver->setXinit(state);  // Contouring::update writes the spline state (contouring.cpp:37,42)
-    for (int k = 0; k < _solver->N; k++)  // :102-108
-        for (auto &module : _modules) module->setParameters(data, _module_data, k);
+    {
+        PROFILE_SCOPE("SetParameters");  // :101
+        for (int k = 0; k < _solver->N; k++)  // :102-108
+            for (auto &module : _modules) module->setParameters(data, _module_data, k);
+    }
 
     _warmstart = Trajectory();
     for (int k = 0; k < _solver->N; k++) _warmstart.add(_solver->getEgoPrediction(k, "x"), _solver->getEgoPrediction(k, "y"));
@@ -69,11 +77,14 @@ PlannerOutput Planner::solveMPC(State &state, RealTimeData &data) {  // :37-158
     _solver->_params.solver_timeout = remainingPlanningTime(data, 1. / CONFIG().control_frequency, 0.006);  // :117-118
 
     int exit_flag = EXIT_CODE_NOT_OPTIMIZED_YET;  // :125-133
-    for (auto &module : _modules) {
-        exit_flag = module->optimize(state, data, _module_data);
-        if (exit_flag != EXIT_CODE_NOT_OPTIMIZED_YET) break;
+    {
+        PROFILE_SCOPE("Optimization");  // :123
+        for (auto &module : _modules) {
+            exit_flag = module->optimize(state, data, _module_data);
+            if (exit_flag != EXIT_CODE_NOT_OPTIMIZED_YET) break;
+        }
+        if (exit_flag == EXIT_CODE_NOT_OPTIMIZED_YET) exit_flag = _solver->solve();
     }
-    if (exit_flag == EXIT_CODE_NOT_OPTIMIZED_YET) exit_flag = _solver->solve();
     last_exit_flag = exit_flag;
 
     if (exit_flag != 1) {  // :140-146

@@ -206,7 +206,7 @@ def make_scene_batch(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int, seed: 
             for o in range(n_gau):  # gaussian_constraints.cpp:31-79
                 pre = f"gaussian_obst_{o}_"
                 if k == 0:
-                    vals = dict(x=pos0[0] + 50, y=pos0[1] + 50, major=0.1, minor=0.1, risk=0.05, r=0.1)
+                    vals = dict(x=pos0[0] + 100, y=pos0[1] + 100, major=0.1, minor=0.1, risk=0.05, r=0.1)  # (:23-29, 39-52)
                 else:
                     vals = dict(x=obs_pos[o, k, 0], y=obs_pos[o, k, 1], major=max(sigma[k - 1], 1e-3), minor=max(sigma[k - 1], 1e-3),
                                 risk=0.05, r=OBSTACLE_RADIUS)
@@ -371,3 +371,49 @@ def make_scene_batch_chunked(spec: pb.ProblemSpec, n_scenes: int, n_guesses: int
     for k in ("xinit", "x0", "params"):
         out[k] = np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=0))
     return out
+
+
+def compact_scene(spec: pb.ProblemSpec, batch, n_scenes: int, n_guesses: int):
+    """The compact scene description `mpcgpu_solve_tmpc_scene_host` consumes, recovered from a full batch: what the
+    modules' setParameters READ (obstacle predictions, radii, polyhedra rows, the stage-invariant weights / spline / disc
+    parameters) instead of the N x npar parameter matrix they write.  Returns a dict with base_params [S, npar],
+    obstacles [S, n_obs, N, 5], obstacle_radius [S, n_obs], obstacle_flags [S, n_obs], risk, halfspaces [S, N, n_hs, 3] or
+    None, guided [G], xinit [S, nx]."""
+    S, G, N, npar, nx = n_scenes, n_guesses, spec.N, spec.npar, spec.nx
+    pm = spec.parameter_map()
+    kinds = dict(spec.constraints)
+    par = batch["params"].reshape(S, G, N, npar)[:, 0]  # guess 0 = the main solver's parameters of the control step
+    base = par[:, 1].copy()
+    n_ell, n_gau, n_dec = kinds.get(pb.CON_ELLIPSOID, 0), kinds.get(pb.CON_GAUSSIAN, 0), kinds.get(pb.CON_DECOMP, 0)
+    n_obs = max(n_ell, n_gau)
+    obstacles = np.zeros((S, n_obs, N, 5))
+    radius = np.zeros((S, n_obs))
+    flags = np.zeros((S, n_obs), dtype=np.int32)
+    risk = 0.05
+    for o in range(n_obs):
+        if n_ell:
+            for c, nm in enumerate(("x", "y", "psi", "major", "minor")):
+                obstacles[:, o, : N - 1, c] = par[:, 1:, pm[f"ellipsoid_obst_{o}_{nm}"]]
+            radius[:, o] = par[:, 1, pm[f"ellipsoid_obst_{o}_r"]]
+            gauss = par[:, 1, pm[f"ellipsoid_obst_{o}_chi"]] != 1.0
+            flags[:, o] = gauss.astype(np.int32)
+            if gauss.any():
+                risk = float(np.exp(-0.5 * par[gauss, 1, pm[f"ellipsoid_obst_{o}_chi"]][0]))
+        else:
+            obstacles[:, o, : N - 1, 0] = par[:, 1:, pm[f"gaussian_obst_{o}_x"]]
+            obstacles[:, o, : N - 1, 1] = par[:, 1:, pm[f"gaussian_obst_{o}_y"]]
+            obstacles[:, o, : N - 1, 3] = par[:, 1:, pm[f"gaussian_obst_{o}_major"]]
+            obstacles[:, o, : N - 1, 4] = par[:, 1:, pm[f"gaussian_obst_{o}_minor"]]
+            radius[:, o] = par[:, 1, pm[f"gaussian_obst_{o}_r"]]
+            flags[:, o] = 1
+            risk = float(par[0, 1, pm[f"gaussian_obst_{o}_risk"]])
+        obstacles[:, o, N - 1] = obstacles[:, o, N - 2]  # the last prediction step feeds no stage
+    halfspaces = None
+    if n_dec:
+        halfspaces = np.zeros((S, N, n_dec, 3))
+        for i in range(n_dec):
+            for c, nm in enumerate(("a1", "a2", "b")):
+                halfspaces[:, :, i, c] = par[:, :, pm[f"disc_0_decomp_{i}_{nm}"]]
+    guided = np.array([0] + [1] * (G - 1), dtype=np.int32)
+    return dict(base_params=base, obstacles=obstacles, obstacle_radius=radius, obstacle_flags=flags, risk=risk, halfspaces=halfspaces,
+                guided=guided, xinit=batch["xinit"].reshape(S, G, nx)[:, 0].copy())

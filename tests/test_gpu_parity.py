@@ -100,3 +100,37 @@ def test_device_side_topology_constraints_match_host_packing(binding):
     np.testing.assert_allclose([i["pobj"] for i, o in zip(info2, ok) if o], [i["pobj"] for i, o in zip(info, ok) if o], rtol=1e-7)
     np.testing.assert_array_equal(best2, best)
     solver.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg2", "cfg2_gaussian", "cfg3"])
+def test_device_side_scene_packing_reproduces_the_reference_parameter_matrix_and_the_oracle_solution(name):
+    """the whole per-stage parameter vector is built on the device from the compact scene description
+    (mpcgpu_solve_tmpc_scene_host).  (1) The packed blocks equal, slot by slot, what the reference-semantics packer writes
+    on the host (scenes.make_scene_batch: stage-0 dummies, prediction step k-1 -> stage k, topology halfspaces of the guided
+    guesses, decomp rows); (2) the solves equal the ORACLE run directly on that parameter matrix."""
+    from mpc_planner_b200 import binding
+
+    spec = pb.CONFIGS[name]()
+    S, G = 3, 4
+    b = scenes.make_scene_batch(spec, S, G, seed=12, gaussian_obstacles=(name == "cfg2_gaussian"))
+    cs = scenes.compact_scene(spec, b, S, G)
+    solver = binding.BatchSolver(spec, S * G)
+    xt, ut, info, best = solver.solve_tmpc_scene(cs["xinit"], b["x0"], cs["base_params"], cs["obstacles"], cs["obstacle_radius"],
+                                                 cs["obstacle_flags"], cs["guided"], risk=cs["risk"], halfspaces=cs["halfspaces"],
+                                                 robot_radius=scenes.ROBOT_RADIUS)
+    packed = solver.packed_params(S * G)
+    np.testing.assert_allclose(packed, b["params"], rtol=1e-12, atol=1e-12)
+    oxt, out, oinfo = oracle.solve_batch(spec, b["xinit"], b["x0"], b["params"])
+    n_ok = 0
+    for i in range(S * G):
+        assert same_status(info[i], oinfo[i]), (i, info[i], oinfo[i])
+        if oinfo[i]["exit_code"] == 1:
+            n_ok += 1
+            np.testing.assert_allclose(xt[i], oxt[i], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(ut[i], out[i], rtol=1e-6, atol=1e-6)
+    assert n_ok >= S
+    for s in range(S):
+        ob = oracle.find_best(oinfo[s * G:(s + 1) * G])
+        assert (best[s] >= 0) == (ob >= 0)
+    solver.close()
