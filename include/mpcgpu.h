@@ -41,8 +41,12 @@ enum mpcgpu_model {
 
 /* Path-tracking objective, mpc_planner_modules/scripts */
 enum mpcgpu_objective {
-    MPCGPU_OBJ_CONTOURING = 0,     /* contouring.py:48-98 (MPCC)                                 */
-    MPCGPU_OBJ_CURVATURE_AWARE = 1 /* curvature_aware_contouring.py:48-105 (CA-MPC cost)         */
+    MPCGPU_OBJ_CONTOURING = 0,      /* contouring.py:48-98 (MPCC)                                 */
+    MPCGPU_OBJ_CURVATURE_AWARE = 1, /* curvature_aware_contouring.py:48-105 (CA-MPC cost)         */
+    MPCGPU_OBJ_GENERATED = 2,       /* stage cost emitted by mpc_planner_b200/codegen.py from the module scripts (any objective
+                                       stack); only per-problem libraries built with that header have such a kernel          */
+    MPCGPU_OBJ_GOAL = 3             /* MPCBase(a, w) + goal_module.py:26-41 (configuration_lmpcc): hand-restated in the CPU
+                                       oracle only, as the checker of the GENERATED kernel of that stack                      */
 };
 
 /* Constraint blocks, in module order (solver_definition.py:36-49) */
@@ -51,7 +55,9 @@ enum mpcgpu_constraint_kind {
     MPCGPU_CON_ELLIPSOID = 1, /* ellipsoid_constraints.py:65-119  d' M d >= 1                     */
     MPCGPU_CON_GAUSSIAN = 2,  /* gaussian_constraints.py:68-117   chance constraint >= 0          */
     MPCGPU_CON_DECOMP = 3,    /* decomp_constraints.py:68-98      a.disc - (b + slack) <= 0       */
-    MPCGPU_CON_SCENARIO = 4   /* scenario_constraints.py:64-94    a.disc - (b + slack) <= 0       */
+    MPCGPU_CON_SCENARIO = 4,  /* scenario_constraints.py:64-94    a.disc - (b + slack) <= 0       */
+    MPCGPU_CON_GENERATED = 5  /* all rows emitted by mpc_planner_b200/codegen.py (one block, con_count = nh; rows may depend on
+                                 x, y, psi and the slack state only; their bound side comes with the generated code)         */
 };
 
 /*
@@ -102,6 +108,7 @@ typedef struct mpcgpu_problem_desc {
                            bound (the slack state of the slack models: zero dynamics, x0 = 0 = lower bound) keep an
                            interior; same purpose as IPOPT's bound_relax_factor */
     double res_eq_fail; /* res_eq above this demotes success (acados_solver_interface.cpp:176-181) */
+    int p_goal;         /* MPCGPU_OBJ_GOAL: first of goal_weight, goal_x, goal_y (goal_module.py:19-22); else -1 */
 } mpcgpu_problem_desc;
 
 /* Per-solve result record (`AcadosInfo`, acados_solver_interface.h:96-125) */

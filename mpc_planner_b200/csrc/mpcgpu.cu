@@ -373,6 +373,8 @@ static bool desc_is_valid(const mpcgpu_problem_desc &d) {
     if (d.qp_warm_start != 0 && (!(d.qp_ws_thr > 0.0) || !(d.qp_ws_mu > 0.0))) return false;
     auto in_range = [&](int idx, int extent) { return idx >= 0 && extent >= 1 && idx + extent <= d.npar; };
     auto optional = [&](int idx) { return idx == -1 || in_range(idx, 1); };
+    const bool gen_obj = (d.objective == MPCGPU_OBJ_GENERATED);  // emitted code: its parameter indices are compiled in
+    if (!gen_obj) {
     if (!in_range(d.p_acceleration, 1) || !in_range(d.p_angular_velocity, 1)) return false;
     if (!optional(d.p_slack) || !optional(d.p_ego_disc_offset)) return false;
     const bool needs_vref = d.weigh_velocity != 0 || d.objective == MPCGPU_OBJ_CURVATURE_AWARE;
@@ -381,6 +383,7 @@ static bool desc_is_valid(const mpcgpu_problem_desc &d) {
     if (!in_range(d.p_contour, 1)) return false;
     if (d.objective == MPCGPU_OBJ_CONTOURING ? !in_range(d.p_lag, 1) : !optional(d.p_lag)) return false;
     if (d.n_segments < 1 || !in_range(d.p_spline, 9 * d.n_segments)) return false;
+    }
     if (d.n_con_modules < 0 || d.n_con_modules > 3) return false;
     int rows = 0;
     bool needs_disc = false;
@@ -392,9 +395,11 @@ static bool desc_is_valid(const mpcgpu_problem_desc &d) {
         case MPCGPU_CON_GAUSSIAN: stride = 6; needs_disc = true; break;
         case MPCGPU_CON_DECOMP:
         case MPCGPU_CON_SCENARIO: break;
+        case MPCGPU_CON_GENERATED: stride = 0; break;
         default: return false;
         }
-        if (d.con_count[m] < 1 || !in_range(d.con_param[m], stride * d.con_count[m])) return false;
+        if (d.con_count[m] < 1) return false;
+        if (stride > 0 && !in_range(d.con_param[m], stride * d.con_count[m])) return false;
         rows += d.con_count[m];
     }
     if (rows != d.nh) return false;

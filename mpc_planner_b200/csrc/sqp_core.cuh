@@ -317,9 +317,8 @@ MPC_HD void linearize_part(const PA &pa, const Layout &L, double *st, const doub
             const int lo = (NH * q) / 4, hi = (NH * (q + 1)) / 4;
             stage_constraints<CFG, true>(pa, L, z, st + S::RH, st + S::JR, st + S::LAM + 2 * NZ, Hx, lo, hi);
             for (int j = lo; j < hi; j++) {  // fold the bound side: row value s (h - bound) >= 0, gradient s dh
-                const int kind = row_kind<CFG>(j);
-                const double sgn = row_sign<CFG>(kind);
-                st[S::RH + j] = sgn * (st[S::RH + j] - row_bound<CFG>(kind)) + L.qp_relax;
+                const double sgn = row_sign_of<CFG>(j);
+                st[S::RH + j] = sgn * (st[S::RH + j] - row_bound_of<CFG>(j)) + L.qp_relax;
                 st[S::JR + 3 * j] *= sgn;
                 st[S::JR + 3 * j + 1] *= sgn;
                 st[S::JR + 3 * j + 2] *= sgn;

@@ -23,8 +23,8 @@ MAX_NZ = 9
 MAX_CON_MODULES = 4
 
 MODEL_UNICYCLE, MODEL_UNICYCLE_SLACK, MODEL_BICYCLE = 0, 1, 2
-OBJ_CONTOURING, OBJ_CURVATURE_AWARE = 0, 1
-CON_LINEAR, CON_ELLIPSOID, CON_GAUSSIAN, CON_DECOMP, CON_SCENARIO = 0, 1, 2, 3, 4
+OBJ_CONTOURING, OBJ_CURVATURE_AWARE, OBJ_GENERATED, OBJ_GOAL = 0, 1, 2, 3
+CON_LINEAR, CON_ELLIPSOID, CON_GAUSSIAN, CON_DECOMP, CON_SCENARIO, CON_GENERATED = 0, 1, 2, 3, 4, 5
 
 
 class ProblemDesc(ctypes.Structure):
@@ -69,6 +69,7 @@ class ProblemDesc(ctypes.Structure):
         ("qp_ws_mu", ctypes.c_double),
         ("qp_relax", ctypes.c_double),
         ("res_eq_fail", ctypes.c_double),
+        ("p_goal", ctypes.c_int),
     ]
 
 
@@ -316,6 +317,7 @@ class ProblemSpec:
         d.res_eq_fail = self.res_eq_fail
         d.qp_warm_start, d.qp_ws_thr, d.qp_ws_mu = self.qp_warm_start, self.qp_ws_thr, self.qp_ws_mu
         d.qp_relax = self.qp_relax
+        d.p_goal = -1
         return d
 
     # sizes of the reference's flat arrays (AcadosParameters, acados_solver_interface.h:51-56)
@@ -327,6 +329,84 @@ class ProblemSpec:
             xtraj=self.nx * (self.N + 1),
             utraj=self.nu * self.N,
         )
+
+
+@dataclass
+class GeneratedSpec(ProblemSpec):
+    """A module stack whose stage functions were EMITTED by mpc_planner_b200/codegen.py (`stage_<name>.cuh` + `.json`): the
+    parameter map, bounds and row sides are the ones the reference's own `define_parameters` / `constraint_*_bounds`
+    produced when the generator traced the stack.  `oracle_objective` (optional) names the hand-restated objective the CPU
+    oracle checks this stack with."""
+
+    gen: dict = field(default_factory=dict)
+    oracle_objective: int = OBJ_GENERATED
+
+    @staticmethod
+    def load(name, directory=None, **kw):
+        import json
+        import os
+
+        directory = directory or os.path.join(os.path.dirname(os.path.abspath(__file__)), "generated_stacks")
+        with open(os.path.join(directory, f"stage_{name}.json")) as f:
+            g = json.load(f)
+        model = {("a", "w", "x", "y", "psi", "v", "spline"): MODEL_UNICYCLE, ("a", "w", "x", "y", "psi", "v", "spline", "slack"): MODEL_UNICYCLE_SLACK}[
+            tuple(g["inputs"] + g["states"])]
+        return GeneratedSpec("generated_" + name, model=model, objective=OBJ_GENERATED, N=g["N"], n_segments=g["n_segments"],
+                             constraints=[(CON_GENERATED, g["nh"])], gen=g, **kw)
+
+    def header(self, directory=None):
+        import os
+
+        directory = directory or os.path.join(os.path.dirname(os.path.abspath(__file__)), "generated_stacks")
+        return os.path.join(directory, f"stage_{self.gen['name']}.cuh")
+
+    def parameter_map(self):
+        return dict(self.gen["parameter_map"])
+
+    def parameter_bundles(self):
+        return {k: [v] for k, v in self.gen["parameter_map"].items()}
+
+    def constraint_first_param(self):
+        return [0]
+
+    def constraint_bounds(self):
+        lh = [(-math.inf if v <= -1e14 else v) for v in self.gen["lh"]]
+        uh = [(math.inf if v >= 1e14 else v) for v in self.gen["uh"]]
+        return lh, uh
+
+    def desc(self, for_oracle=False) -> ProblemDesc:
+        pm = self.parameter_map()
+        d = ProblemDesc()
+        d.model, d.objective, d.N = self.model, self.objective, self.N
+        d.nx, d.nu, d.npar, d.nh = self.nx, self.nu, len(pm), self.nh
+        d.dt, d.erk_steps, d.n_segments = self.dt, 3, self.n_segments
+        for f in ("p_acceleration", "p_angular_velocity", "p_slack", "p_velocity", "p_reference_velocity", "p_contour", "p_lag", "p_spline",
+                  "p_ego_disc_radius", "p_ego_disc_offset", "p_goal"):
+            setattr(d, f, -1)
+        d.weigh_velocity = 0
+        d.n_con_modules = 1
+        d.con_kind[0], d.con_count[0], d.con_param[0] = CON_GENERATED, self.nh, 0
+        lo, up = _MODELS[self.model]["lower"], _MODELS[self.model]["upper"]
+        for i in range(self.nz):
+            d.lower_bound[i], d.upper_bound[i] = lo[i], up[i]
+        d.n_sqp, d.qp_iter_max, d.qp_tol = self.n_sqp, self.qp_iter_max, self.qp_tol
+        d.reg_epsilon, d.qp_mu0, d.qp_thr0 = self.reg_epsilon, self.qp_mu0, self.qp_thr0
+        d.res_eq_fail = self.res_eq_fail
+        d.qp_warm_start, d.qp_ws_thr, d.qp_ws_mu = self.qp_warm_start, self.qp_ws_thr, self.qp_ws_mu
+        d.qp_relax = self.qp_relax
+        if for_oracle:
+            # the hand-restated NLP the oracle checks this stack with (same parameter vector)
+            d.objective = self.oracle_objective
+            d.p_acceleration, d.p_angular_velocity = pm["acceleration"], pm["angular_velocity"]
+            if self.oracle_objective == OBJ_GOAL:
+                d.p_goal = pm["goal_weight"]
+                assert pm["goal_x"] == d.p_goal + 1 and pm["goal_y"] == d.p_goal + 2
+                n = sum(1 for k in pm if k.startswith("ellipsoid_obst_") and k.endswith("_x"))
+                d.con_kind[0], d.con_count[0], d.con_param[0] = CON_ELLIPSOID, n, pm["ellipsoid_obst_0_x"]
+                d.p_ego_disc_radius, d.p_ego_disc_offset = pm["ego_disc_radius"], pm["ego_disc_0_offset"]
+            else:
+                raise ValueError("no oracle restatement for this generated stack")
+        return d
 
 
 # ---- the BASELINE.json configs (SURVEY.md section 8 table) ----

@@ -12,11 +12,13 @@ _lib = None
 _dp = ctypes.POINTER(ctypes.c_double)
 
 
-def build_generated(registry_header, out):
-    """Host emulation of a GENERATED kernel instantiation (generate.generate_cuda_registry)."""
+def build_generated(registry_header, out, stage_header=None):
+    """Host emulation of a GENERATED kernel instantiation (generate.generate_cuda_registry); `stage_header`: stage
+    functions emitted by codegen.py."""
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    extra = ['-DMPCGPU_GENERATED_STAGE="%s"' % os.path.abspath(stage_header)] if stage_header else []
     subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(_ROOT, "include"),
-                           '-DMPCGPU_GENERATED_REGISTRY="%s"' % os.path.abspath(registry_header), "-o", out, os.path.join(_HERE, "emu.cpp")])
+                           '-DMPCGPU_GENERATED_REGISTRY="%s"' % os.path.abspath(registry_header)] + extra + ["-o", out, os.path.join(_HERE, "emu.cpp")])
     return out
 
 

@@ -45,8 +45,10 @@ from curvature_aware_contouring import CurvatureAwareContouringModule  # noqa: E
 from decomp_constraints import DecompConstraintModule  # noqa: E402
 from ellipsoid_constraints import EllipsoidConstraintModule  # noqa: E402
 from gaussian_constraints import GaussianConstraintModule  # noqa: E402
+from goal_module import GoalModule  # noqa: E402
 from guidance_constraints import GuidanceConstraintModule  # noqa: E402
 from mpc_base import MPCBaseModule  # noqa: E402
+from path_reference_velocity import PathReferenceVelocityModule  # noqa: E402
 from scenario_constraints import ScenarioConstraintModule  # noqa: E402
 from solver_definition import (  # noqa: E402
     constraint_lower_bounds,
@@ -113,6 +115,16 @@ def build(name):
         m.add_module(ContouringModule(s))
         m.add_module(ScenarioConstraintModule(s))
         return ContouringSecondOrderUnicycleModelWithSlack(), m, s
+    if name == "lmpcc_goal":  # configuration_lmpcc, generate_jackalsimulator_solver.py:105-121 (Goal objective: generated code only)
+        s = settings_for(20, 4)
+        m = ModuleManager()
+        b = m.add_module(MPCBaseModule(s))
+        b.weigh_variable(var_name="a", weight_names="acceleration")
+        b.weigh_variable(var_name="w", weight_names="angular_velocity")
+        m.add_module(GoalModule(s))
+        m.add_module(PathReferenceVelocityModule(s))
+        m.add_module(EllipsoidConstraintModule(s))
+        return ContouringSecondOrderUnicycleModel(), m, s
     raise KeyError(name)
 
 
@@ -125,6 +137,12 @@ def random_params(pmap, rng):
             p[i] = rng.uniform(0.05, 1.0)
         elif name == "slack":
             p[i] = rng.uniform(10.0, 1000.0)
+        elif name == "goal_weight":
+            p[i] = rng.uniform(0.5, 5.0)
+        elif name in ("goal_x", "goal_y"):
+            p[i] = rng.uniform(-10.0, 20.0)
+        elif name.startswith("spline_v"):
+            p[i] = rng.uniform(-1, 1)
         elif name == "reference_velocity":
             p[i] = rng.uniform(0.5, 2.5)
         elif name in ("terminal_angle", "terminal_contouring"):
@@ -175,7 +193,7 @@ def random_z(model, rng):
 
 def main(M=24):
     out = {}
-    for ci, name in enumerate(["cfg1", "cfg2", "cfg2_gaussian", "cfg3", "cfg4"]):
+    for ci, name in enumerate(["cfg1", "cfg2", "cfg2_gaussian", "cfg3", "cfg4", "lmpcc_goal"]):
         model, modules, settings = build(name)
         params = Parameters()
         define_parameters(modules, params, settings)
