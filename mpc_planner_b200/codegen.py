@@ -319,6 +319,27 @@ def build_stack(name):
         m.add_module(ContouringModule(s))
         m.add_module(GuidanceConstraintModule(s, constraint_submodule=EllipsoidConstraintModule))
         return ContouringSecondOrderUnicycleModel(), m, s
+    if name in ("tmpc_2discs", "tmpc_dynvel"):
+        # configuration_tmpc (generate_jackalsimulator_solver.py:35-58, 94-103) with settings the hand-written templates do not
+        # cover: two ego discs (settings n_discs: 2 -> one ellipsoid row per obstacle and disc, ellipsoid_constraints.py:88-96),
+        # or contouring/dynamic_velocity_reference: true (velocity spline tracked in the contouring cost, contouring.py:61-67,
+        # 80-81, parameters from PathReferenceVelocity)
+        s = settings_for(20, 8)
+        dyn = name == "tmpc_dynvel"
+        if name == "tmpc_2discs":
+            s["n_discs"] = 2
+        s["contouring"]["dynamic_velocity_reference"] = dyn
+        m = ModuleManager()
+        b = m.add_module(MPCBaseModule(s))
+        b.weigh_variable(var_name="a", weight_names="acceleration")
+        b.weigh_variable(var_name="w", weight_names="angular_velocity")
+        if not dyn:
+            b.weigh_variable(var_name="v", weight_names=["velocity", "reference_velocity"], cost_function=lambda x, w: w[0] * (x - w[1]) ** 2)
+        m.add_module(ContouringModule(s))
+        if dyn:
+            m.add_module(PathReferenceVelocityModule(s))
+        m.add_module(GuidanceConstraintModule(s, constraint_submodule=EllipsoidConstraintModule))
+        return ContouringSecondOrderUnicycleModel(), m, s
     if name == "lmpcc_goal":  # configuration_lmpcc, generate_jackalsimulator_solver.py:105-121: Goal objective (no template for it)
         s = settings_for(20, 4)
         m = ModuleManager()
@@ -346,6 +367,6 @@ def generate(name, out_dir=OUT_DIR):
 
 
 if __name__ == "__main__":
-    for nm in (sys.argv[1:] or ["tmpc", "lmpcc_goal"]):
+    for nm in (sys.argv[1:] or ["tmpc", "lmpcc_goal", "tmpc_2discs", "tmpc_dynvel"]):
         hdr, st = generate(nm)
         print(nm, "->", hdr, st)

@@ -1,10 +1,10 @@
 // emu_gen.cpp -- TEST INFRASTRUCTURE: host compile of a GENERATED stage-function header (mpc_planner_b200/codegen.py) next to
 // the hand-derived functions of csrc/stage_functions.cuh, so that the CPU suite can compare the two (and the generated
-// ones against golden values from the reference's Python).  Compile with -DMPCGPU_GEN_HEADER="\"path/stage_<name>.cuh\"".
+// ones against golden values from the reference's Python).  Compile with -DMPCGPU_GENERATED_STAGE="\"path/stage_<name>.cuh\"" (the
+// same switch the per-problem CUDA libraries are built with).
 #include <cstring>
 
-#include "../../mpc_planner_b200/csrc/stage_functions.cuh"
-#include MPCGPU_GEN_HEADER
+#include "../../mpc_planner_b200/csrc/stage_functions.cuh"  // includes the generated header (MPCGPU_GENERATED_STAGE)
 
 using namespace mpcgpu;
 

@@ -115,6 +115,23 @@ def build(name):
         m.add_module(ContouringModule(s))
         m.add_module(ScenarioConstraintModule(s))
         return ContouringSecondOrderUnicycleModelWithSlack(), m, s
+    if name in ("tmpc_2discs", "tmpc_dynvel"):  # configuration_tmpc with n_discs = 2 / dynamic_velocity_reference (generated code only)
+        s = settings_for(20, 8)
+        dyn = name == "tmpc_dynvel"
+        if name == "tmpc_2discs":
+            s["n_discs"] = 2
+        s["contouring"]["dynamic_velocity_reference"] = dyn
+        m = ModuleManager()
+        b = m.add_module(MPCBaseModule(s))
+        b.weigh_variable(var_name="a", weight_names="acceleration")
+        b.weigh_variable(var_name="w", weight_names="angular_velocity")
+        if not dyn:
+            b.weigh_variable(var_name="v", weight_names=["velocity", "reference_velocity"], cost_function=lambda x, w: w[0] * (x - w[1]) ** 2)
+        m.add_module(ContouringModule(s))
+        if dyn:
+            m.add_module(PathReferenceVelocityModule(s))
+        m.add_module(GuidanceConstraintModule(s, constraint_submodule=EllipsoidConstraintModule))
+        return ContouringSecondOrderUnicycleModel(), m, s
     if name == "lmpcc_goal":  # configuration_lmpcc, generate_jackalsimulator_solver.py:105-121 (Goal objective: generated code only)
         s = settings_for(20, 4)
         m = ModuleManager()
@@ -156,7 +173,7 @@ def random_params(pmap, rng):
             p[i] = rng.uniform(-1, 1) * scale + (1.0 if (coef == "c" and name.startswith("spline_x")) else 0.0)
         elif name == "ego_disc_radius":
             p[i] = 0.325
-        elif name == "ego_disc_0_offset":
+        elif name.startswith("ego_disc_") and name.endswith("_offset"):
             p[i] = rng.uniform(-0.3, 0.3)
         elif name.endswith(("_a1", "_a2")):
             p[i] = rng.uniform(-1, 1)
@@ -193,7 +210,7 @@ def random_z(model, rng):
 
 def main(M=24):
     out = {}
-    for ci, name in enumerate(["cfg1", "cfg2", "cfg2_gaussian", "cfg3", "cfg4", "lmpcc_goal"]):
+    for ci, name in enumerate(["cfg1", "cfg2", "cfg2_gaussian", "cfg3", "cfg4", "lmpcc_goal", "tmpc_2discs", "tmpc_dynvel"]):
         model, modules, settings = build(name)
         params = Parameters()
         define_parameters(modules, params, settings)
