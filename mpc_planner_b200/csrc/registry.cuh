@@ -27,8 +27,12 @@ typedef Config<MPCGPU_MODEL_UNICYCLE_SLACK, MPCGPU_OBJ_CURVATURE_AWARE, 30, 5, M
 // cfg 4: SH-MPC scenario halfspaces   generate_jackalsimulator_solver.py:69-91
 typedef Config<MPCGPU_MODEL_UNICYCLE_SLACK, MPCGPU_OBJ_CONTOURING, 20, 5, MPCGPU_CON_SCENARIO, 24> cfg_safe_horizon_n20;
 
+// BASELINE configs[0] as written: BicycleModel2ndOrder (solver_model.py:302-351) + MPCC + 4 ellipsoidal obstacles, N = 20
+typedef Config<MPCGPU_MODEL_BICYCLE, MPCGPU_OBJ_CONTOURING, 20, 5, MPCGPU_CON_ELLIPSOID, 4> cfg_bicycle_n20_o4;
+
 #define MPCGPU_CONFIG_LIST(X) \
     X(cfg_basic_n20_o4)       \
+    X(cfg_bicycle_n20_o4)     \
     X(cfg_tmpc_n20_o8)        \
     X(cfg_tmpc_gauss_n20_o8)  \
     X(cfg_tmpc_n30_o12)       \
@@ -121,17 +125,18 @@ MPC_HD void eval_stage_sample(const Layout &L, const double *z, const double *p,
         }
     }
     if (xnext || AB || dyn_hess) {
-        double xn[NX], BA[NX * NZ], Hd[7] = {0, 0, 0, 0, 0, 0, 0};
-        unicycle_step<CFG>(L, z, xn, BA, pi, (pi && dyn_hess) ? Hd : nullptr);
+        double xn[NX], BA[NX * NZ], Hd[CFG::NHD];
+        for (int e = 0; e < CFG::NHD; e++) Hd[e] = 0.0;
+        model_step<CFG>(L, z, xn, BA, pi, (pi && dyn_hess) ? Hd : nullptr);
         if (xnext) for (int i = 0; i < NX; i++) xnext[i] = xn[i];
         if (AB) for (int i = 0; i < NX * NZ; i++) AB[i] = BA[i];
         if (dyn_hess) {
             for (int i = 0; i < NZ * NZ; i++) dyn_hess[i] = 0.0;
-            const int ia[7] = {CFG::IPSI, CFG::IPSI, CFG::IW, CFG::IPSI, CFG::IPSI, CFG::IW, CFG::IW};
-            const int ib[7] = {CFG::IPSI, CFG::IW, CFG::IW, CFG::IV, CFG::IA, CFG::IV, CFG::IA};
-            for (int e = 0; e < 7; e++) {
-                dyn_hess[ia[e] * NZ + ib[e]] = Hd[e];
-                dyn_hess[ib[e] * NZ + ia[e]] = Hd[e];
+            for (int e = 0; e < CFG::NHD; e++) {
+                int hi, hj;
+                dyn_hess_pair<CFG>(e, hi, hj);
+                dyn_hess[hi * NZ + hj] = Hd[e];
+                dyn_hess[hj * NZ + hi] = Hd[e];
             }
         }
     }

@@ -126,7 +126,8 @@ template <class CFG>
 struct SL {
     static constexpr int NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NH = CFG::NH, NROW = CFG::NROW;
     static constexpr int NHP = NZ * (NZ + 1) / 2, NPP = NX * (NX + 1) / 2;
-    static constexpr int NE = 2;                // columns of A that differ from the identity (psi, v)
+    static constexpr int NE = CFG::NE;          // columns of A that differ from the identity: (psi, v) / (psi, v, delta)
+    static constexpr int NLUU = NU * (NU + 1) / 2;  // Cholesky factor of M_uu: packed lower, RECIPROCAL diagonal
     static constexpr int Z = 0;                 // NLP iterate [u;x]
     static constexpr int LAM = Z + NZ;          // inequality multipliers (IPM variable = NLP multiplier after the QP)
     static constexpr int T = LAM + NROW;        // IPM slacks
@@ -150,21 +151,25 @@ struct SL {
     static constexpr int PV = PC + NX;          // Riccati cost-to-go vector
     static constexpr int YV = PV + NX;          // L_uu^-1 m_u
     static constexpr int LXU = YV + NU;         // L_xu = M_xu L_uu^-T, NX x NU
-    static constexpr int LUU = LXU + NU * NX;   // Cholesky factor of M_uu as {1/l00, l10, 1/l11}
-    static constexpr int DZ = LUU + 3;          // QP primal iterate
+    static constexpr int LUU = LXU + NU * NX;   // Cholesky factor of M_uu as {1/l00, l10, 1/l11 (, l20, l21, 1/l22)}
+    static constexpr int DZ = LUU + NLUU;       // QP primal iterate
     static constexpr int DPI = DZ + NZ;         // equality multipliers: QP iterate during the IPM, NLP multiplier pi_k
                                                 // of the equation defining x_k between QPs (read by the linearisation)
     static constexpr int PI = DPI;
     static constexpr int DZN = DPI + NX;        // Newton target (primal)
     static constexpr int PIN = DZN + NZ;        // Newton target (equality multiplier)
-    static constexpr int RAW = PIN + NX;
+    // MIRROR work space of the CTA-parallel Jacobi: the working copy of the block lives in the T / TINV / CORR rows (dead
+    // between QPs) when they hold NZ x NZ doubles, else in an extra area behind the stage image (bicycle with few rows)
+    static constexpr int MIR_EXTRA = (3 * NROW >= NZ * NZ) ? 0 : NZ * NZ;
+    static constexpr int MW = MIR_EXTRA ? PIN + NX : T;
+    static constexpr int RAW = PIN + NX + MIR_EXTRA;
     static constexpr int STRIDE = RAW | 1;      // odd
     // linearisation scratch inside the work area (dead while linearising): partial Hessians.  It must not touch
     // DPI (= pi, read by the dynamics part of the NEXT stage's... of this stage's predecessor)
     static constexpr int LS_HC = WK;            // cost Hessian (packed lower NZ)   -- written by the cost part
     static constexpr int LS_GC = LS_HC + NHP;   // cost gradient NZ
-    static constexpr int LS_HD = LS_GC + NZ;    // dynamics Hessian entries (7)
-    static constexpr int LS_HX = LS_HD + 7;     // constraint Hessian parts: 4 x 6
+    static constexpr int LS_HD = LS_GC + NZ;    // dynamics Hessian entries (CFG::NHD)
+    static constexpr int LS_HX = LS_HD + CFG::NHD;  // constraint Hessian parts: 4 x 6
     static constexpr int LS_END = LS_HX + 24;
     static_assert(LS_END <= DPI, "linearisation scratch must stay below the multipliers pi (stages k < N only)");
     // per-CTA scratch.  On the device it lives inside the terminal stage's unused rows area ([LAM, WK): the terminal
@@ -301,12 +306,12 @@ MPC_HD void linearize_part(const PA &pa, const Layout &L, double *st, const doub
 #pragma unroll
         for (int i = 0; i < NZ; i++) st[S::LS_GC + i] = g[i];
     } else if (part == 1) {
-        double xn[NX], pin[NX], Hd[7];
+        double xn[NX], pin[NX], Hd[CFG::NHD];
 #pragma unroll
         for (int i = 0; i < NX; i++) pin[i] = st_next[S::PI + i];
-        unicycle_step<CFG>(L, z, xn, nullptr, pin, Hd, st + S::BB, st + S::BE);
+        model_step<CFG>(L, z, xn, nullptr, pin, Hd, st + S::BB, st + S::BE);
 #pragma unroll
-        for (int i = 0; i < 7; i++) st[S::LS_HD + i] = Hd[i];
+        for (int i = 0; i < CFG::NHD; i++) st[S::LS_HD + i] = Hd[i];
 #pragma unroll
         for (int i = 0; i < NX; i++) st[S::C + i] = xn[i] - st_next[S::Z + CFG::NU + i];
     } else {
@@ -336,14 +341,13 @@ MPC_HD void assemble_stage(const Layout &L, double *st) {
     double Hp[S::NHP];
 #pragma unroll
     for (int i = 0; i < S::NHP; i++) Hp[i] = st[S::LS_HC + i];
-    // dynamics: second derivatives over (a, w, psi, v), order as written by unicycle_step
-    Hp[trisym(CFG::IPSI, CFG::IPSI)] += st[S::LS_HD + 0];
-    Hp[trisym(CFG::IPSI, CFG::IW)] += st[S::LS_HD + 1];
-    Hp[trisym(CFG::IW, CFG::IW)] += st[S::LS_HD + 2];
-    Hp[trisym(CFG::IPSI, CFG::IV)] += st[S::LS_HD + 3];
-    Hp[trisym(CFG::IPSI, CFG::IA)] += st[S::LS_HD + 4];
-    Hp[trisym(CFG::IW, CFG::IV)] += st[S::LS_HD + 5];
-    Hp[trisym(CFG::IW, CFG::IA)] += st[S::LS_HD + 6];
+    // dynamics: pi-weighted second derivatives over the variables Phi is nonlinear in, order as written by model_step
+#pragma unroll
+    for (int e = 0; e < CFG::NHD; e++) {
+        int hi, hj;
+        dyn_hess_pair<CFG>(e, hi, hj);
+        Hp[trisym(hi, hj)] += st[S::LS_HD + e];
+    }
     {
         const int idx[3] = {CFG::IX, CFG::IY, CFG::IPSI};
 #pragma unroll
@@ -362,11 +366,13 @@ MPC_HD void assemble_stage(const Layout &L, double *st) {
     {   // block structure flag for mirror_stage (DZN is dead between QPs and outside the linearisation scratch)
         const int ia[4] = {CFG::IA, CFG::IW, CFG::IPSI, CFG::IV};
         const int ib[4] = {CFG::IX, CFG::IY, CFG::IS, CFG::HAS_SLACK ? CFG::ISLACK : 0};
-        bool decoupled = (CFG::OBJ == MPCGPU_OBJ_CONTOURING);
+        bool decoupled = (CFG::OBJ == MPCGPU_OBJ_CONTOURING) && !CFG::BICYCLE;
+        if constexpr (!CFG::BICYCLE) {
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+            for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int b = 0; b < NZ - 4; b++) decoupled = decoupled && (Hp[trisym(ia[a], ib[b])] == 0.0);
+                for (int b = 0; b < NZ - 4; b++) decoupled = decoupled && (Hp[trisym(ia[a], ib[b])] == 0.0);
+        }
         static_assert(S::DZN >= S::LS_END, "flag must not overlap the linearisation scratch");
         st[S::DZN] = decoupled ? 1.0 : 0.0;
     }
@@ -381,13 +387,13 @@ MPC_HD void mirror_stage(const Layout &L, double *st, int part) {
     typedef SL<CFG> S;
     constexpr int NZ = CFG::NZ;
     // Jacobi work space of the general path: M in the (dead between QPs) T/TINV/CORR rows area, V in the IPM work area
-    static_assert(3 * S::NROW >= NZ * NZ && S::RAW - S::WK >= NZ * NZ, "MIRROR work space");
-    constexpr bool BLOCKS = (CFG::OBJ == MPCGPU_OBJ_CONTOURING);
+    static_assert(S::DZN - S::WK >= NZ * NZ, "MIRROR work space");
+    constexpr bool BLOCKS = (CFG::OBJ == MPCGPU_OBJ_CONTOURING) && !CFG::BICYCLE;
     constexpr int NA = 4, NB = NZ - NA;
     const int ia[4] = {CFG::IA, CFG::IW, CFG::IPSI, CFG::IV};
     const int ib[4] = {CFG::IX, CFG::IY, CFG::IS, CFG::HAS_SLACK ? CFG::ISLACK : 0};
     double *Hp = st + S::H;
-    if (BLOCKS) {
+    if constexpr (BLOCKS) {
         if (st[S::DZN] == 1.0) {  // written by assemble_stage: exactly block diagonal (part 0 may set 2 concurrently)
             if (part == 0) mirror_subblock<NA>(Hp, L.reg_epsilon, ia);
             else mirror_subblock<NB>(Hp, L.reg_epsilon, ib);
@@ -406,7 +412,8 @@ MPC_HD void mirror_stage(const Layout &L, double *st, int part) {
 // commute: all column updates (A <- A J, V <- V J) of a round, barrier, all row updates (A <- J' A), barrier.  The three
 // entries a rotation is computed from are only ever changed by that pair itself, so no barrier is needed before them.
 // Serial (one thread per stage, 28 rotations per sweep of an 8 x 8 block) this was 32 % of a cfg 3 solve.
-//   work space per stage: Mw = st[T..] (NZ x NZ, dead between QPs), Vw = st[WK..] (NZ x NZ), (c, s) of the round behind Vw.
+//   work space per stage: Mw = st[MW..] (NZ x NZ: the T / TINV / CORR rows, dead between QPs, or an extra area), Vw = st[WK..]
+//   (NZ x NZ), (c, s) of the round behind Vw.
 // ---------------------------------------------------------------------------------------------
 MPC_HD void tournament_pair(int m, int r, int j, int &p, int &q) {
     if (j == 0) {
@@ -426,7 +433,7 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
     constexpr int M = (NZ + 1) & ~1, G = M / 2;  // rounds use M indices (index NZ is a dummy when NZ is odd); G pairs per round
     constexpr int CS = S::WK + NZ * NZ;          // (c, s) of the current round: 2 G doubles
     static_assert(N * G <= NT, "one thread per (stage, pair of the round)");
-    static_assert(3 * S::NROW >= NZ * NZ && S::DZN - S::WK >= NZ * NZ + 2 * G, "MIRROR work space");
+    static_assert(S::DZN - S::WK >= NZ * NZ + 2 * G, "MIRROR work space");
     const double eps = L.reg_epsilon;
     // copy the packed block into the work space, V = I (rows split over the G threads of a stage)
     MPC_PHASE
@@ -438,7 +445,7 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
         if (st[S::DZN] == 2.0)
             for (int i = tid % G; i < NZ; i += G)
                 for (int j = 0; j < NZ; j++) {
-                    st[S::T + i * NZ + j] = st[S::H + trisym(i, j)];
+                    st[S::MW + i * NZ + j] = st[S::H + trisym(i, j)];
                     st[S::WK + i * NZ + j] = (i == j) ? 1.0 : 0.0;
                 }
     }
@@ -449,7 +456,7 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
         if (tid < N * G && tid % G == 0) {  // convergence of each flagged stage (same rule as the register Jacobi)
             double *st = sm + (tid / G) * S::STRIDE;
             if (st[S::DZN] == 2.0) {
-                const double *Mw = st + S::T;
+                const double *Mw = st + S::MW;
                 double offd = 0.0, diag = 0.0;
                 for (int i = 0; i < NZ; i++) {
                     diag += Mw[i * NZ + i] * Mw[i * NZ + i];
@@ -470,7 +477,7 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
                 tournament_pair(M, r, j, p, q);
                 double c = 1.0, sn = 0.0;
                 if (st[S::DZN] == 2.0 && q < NZ) {
-                    double *Mw = st + S::T, *Vw = st + S::WK;
+                    double *Mw = st + S::MW, *Vw = st + S::WK;
                     const double apq = Mw[p * NZ + q], app = Mw[p * NZ + p], aqq = Mw[q * NZ + q];
                     if (!(fabs(apq) <= 1e-19 * (fabs(app) + fabs(aqq)))) {  // rotations that cannot change the diagonal are skipped
                         jacobi_rotation(app, aqq, apq, c, sn);
@@ -496,7 +503,7 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
                 tournament_pair(M, r, j, p, q);
                 const double c = st[CS + 2 * j], sn = st[CS + 2 * j + 1];
                 if (st[S::DZN] == 2.0 && q < NZ && sn != 0.0) {
-                    double *Mw = st + S::T;
+                    double *Mw = st + S::MW;
                     for (int k = 0; k < NZ; k++) {
                         const double mpk = Mw[p * NZ + k], mqk = Mw[q * NZ + k];
                         Mw[p * NZ + k] = c * mpk - sn * mqk;
@@ -512,7 +519,7 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
     if (tid < N * G) {
         double *st = sm + (tid / G) * S::STRIDE;
         if (st[S::DZN] >= 2.0) {
-            const double *Mw = st + S::T, *Vw = st + S::WK;
+            const double *Mw = st + S::MW, *Vw = st + S::WK;
             double e[NZ];
             for (int k = 0; k < NZ; k++) {
                 double l = Mw[k * NZ + k];
@@ -542,15 +549,16 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
 // ---------------------------------------------------------------------------------------------
 template <class CFG>
 struct RicIdx {
-    static constexpr int NE = 2;  // columns of A that differ from the identity: psi, v
-    MPC_HD static constexpr int ecol(int c) { return c == 0 ? 2 : 3; }  // x-index of psi, v
-    MPC_HD static constexpr int eidx(int xi) { return xi == 2 ? 0 : (xi == 3 ? 1 : -1); }
+    static constexpr int NE = CFG::NE;  // columns of A that differ from the identity: psi, v (, delta)
+    MPC_HD static constexpr int ecol(int c) { return 2 + c; }  // x-index of psi, v, delta
+    MPC_HD static constexpr int eidx(int xi) { return (xi >= 2 && xi < 2 + NE) ? xi - 2 : -1; }
     // structural non-zeros of the discrete dynamics of the unicycle family (stage_functions.cuh,
     // unicycle_step): rows x=0, y=1, psi=2, v=3, spline=4 (, slack=5: identity row)
     //   E = A - I :  column psi: rows x, y ;  column v: rows x, y, spline
     //   B         :  column a: rows x, y, v, spline ;  column w: rows x, y, psi
-    MPC_HD static constexpr bool enz(int l, int c) { return c == 0 ? (l == 0 || l == 1) : (l == 0 || l == 1 || l == 4); }
-    MPC_HD static constexpr bool bnz(int l, int u) { return u == 0 ? (l == 0 || l == 1 || l == 3 || l == 4) : (l == 0 || l == 1 || l == 2); }
+    // (the bicycle takes the dense sweeps below: every entry counts)
+    MPC_HD static constexpr bool enz(int l, int c) { return CFG::BICYCLE ? true : (c == 0 ? (l == 0 || l == 1) : (l == 0 || l == 1 || l == 4)); }
+    MPC_HD static constexpr bool bnz(int l, int u) { return CFG::BICYCLE ? true : (u == 0 ? (l == 0 || l == 1 || l == 3 || l == 4) : (l == 0 || l == 1 || l == 2)); }
 };
 
 // Backward factorisation: for k = N-1..0   M = H + barrier terms + [B A]' P+ [B A];
@@ -1238,6 +1246,185 @@ MPC_DEV void riccati_factor_mma(double *sm) {
 }
 #endif  // __CUDACC__
 
+// ---------------------------------------------------------------------------------------------
+// Dense Riccati sweeps for models outside the unicycle family (bicycle: nx = 6, nu = 3, A = I + E with three columns):
+// the same recursion as riccati_factor / riccati_solve with every entry of [B A] counted, a general nu x nu Cholesky and
+// run-time loops; one thread (BASELINE configs[0] is a P = 1 problem: latency of the path matters little next to T-MPC).
+// ---------------------------------------------------------------------------------------------
+template <class CFG>
+MPC_DEV void riccati_factor_dense(double *sm) {
+    typedef SL<CFG> S;
+    typedef RicIdx<CFG> R;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
+    static_assert(!CFG::ANY_SLACK_ROWS || !CFG::BICYCLE, "slack rows with the bicycle's slack input: not built");
+    const int serial_tid = (int)sm[S::W_BASE + S::W_STID];
+    MPC_PHASE
+    if (tid == serial_tid) {
+        double Pn[NX][NX], pv[NX];
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < NX; j++) Pn[i][j] = sm[N * S::STRIDE + S::P + trisym(i, j)];
+        for (int i = 0; i < NX; i++) {
+            pv[i] = sm[N * S::STRIDE + S::GT + NU + i];  // terminal: pv_N = gt_N
+            sm[N * S::STRIDE + S::PV + i] = pv[i];
+        }
+        for (int k = N - 1; k >= 0; k--) {
+            double *st = sm + k * S::STRIDE;
+            double *stn = st + S::STRIDE;
+            double F[NX][NZ], W[NX][NZ], q[NX], M[NZ][NZ], m[NZ];
+            for (int l = 0; l < NX; l++) {
+                for (int u = 0; u < NU; u++) F[l][u] = st[S::BB + l * NU + u];
+                for (int j = 0; j < NX; j++) F[l][NU + j] = ((l == j) ? 1.0 : 0.0) + (R::eidx(j) >= 0 ? st[S::BE + l * NE + (R::eidx(j) >= 0 ? R::eidx(j) : 0)] : 0.0);
+            }
+            for (int l = 0; l < NX; l++) {
+                double pc = 0.0;
+                for (int j = 0; j < NX; j++) pc += Pn[l][j] * st[S::C + j];
+                stn[S::PC + l] = pc;
+                q[l] = pv[l] + pc;
+                for (int a = 0; a < NZ; a++) {
+                    double acc = 0.0;
+                    for (int j = 0; j < NX; j++) acc += Pn[l][j] * F[j][a];
+                    W[l][a] = acc;
+                }
+            }
+            for (int a = 0; a < NZ; a++) {
+                for (int b = 0; b <= a; b++) {
+                    double acc = st[S::H + tri(a, b)];
+                    if (a == b) acc += st[S::GD + a];
+                    const int aa = (a == CFG::IX) ? 0 : (a == CFG::IY) ? 1 : (a == CFG::IPSI) ? 2 : -1;
+                    const int ab = (b == CFG::IX) ? 0 : (b == CFG::IY) ? 1 : (b == CFG::IPSI) ? 2 : -1;
+                    if (aa >= 0 && ab >= 0) acc += st[S::GB + trisym(aa, ab)];
+                    for (int l = 0; l < NX; l++) acc += F[l][a] * W[l][b];
+                    M[a][b] = acc;
+                    M[b][a] = acc;
+                }
+                double mv = st[S::GT + a];
+                for (int l = 0; l < NX; l++) mv += F[l][a] * q[l];
+                m[a] = mv;
+            }
+            // L_uu = chol(M_uu): packed lower with reciprocal diagonal
+            double Lu[NU][NU];
+            for (int i = 0; i < NU; i++)
+                for (int j = 0; j <= i; j++) {
+                    double acc = M[i][j];
+                    for (int c = 0; c < j; c++) acc -= Lu[i][c] * Lu[j][c];
+                    Lu[i][j] = (i == j) ? mpc_rsqrt(acc) : acc * Lu[j][j];  // diagonal entries hold 1 / l_ii
+                    st[S::LUU + tri(i, j)] = Lu[i][j];
+                }
+            double y[NU];
+            for (int i = 0; i < NU; i++) {
+                double acc = m[i];
+                for (int c = 0; c < i; c++) acc -= Lu[i][c] * y[c];
+                y[i] = acc * Lu[i][i];
+                st[S::YV + i] = y[i];
+            }
+            double Lx[NX][NU];
+            for (int i = 0; i < NX; i++) {
+                for (int j = 0; j < NU; j++) {
+                    double acc = M[NU + i][j];
+                    for (int c = 0; c < j; c++) acc -= Lx[i][c] * Lu[j][c];
+                    Lx[i][j] = acc * Lu[j][j];
+                    st[S::LXU + i * NU + j] = Lx[i][j];
+                }
+                double p = m[NU + i];
+                for (int c = 0; c < NU; c++) p -= Lx[i][c] * y[c];
+                pv[i] = p;
+                st[S::PV + i] = p;
+            }
+            for (int i = 0; i < NX; i++)
+                for (int j = 0; j <= i; j++) {
+                    double acc = M[NU + i][NU + j];
+                    for (int c = 0; c < NU; c++) acc -= Lx[i][c] * Lx[j][c];
+                    Pn[i][j] = acc;
+                    Pn[j][i] = acc;
+                    st[S::P + tri(i, j)] = acc;
+                }
+        }
+    }
+    MPC_PHASE_END
+}
+
+template <class CFG>
+MPC_DEV void riccati_solve_dense(double *sm, bool BACKWARD) {
+    typedef SL<CFG> S;
+    typedef RicIdx<CFG> R;
+    constexpr int N = CFG::N, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
+    double *W = sm + S::W_BASE;
+    const int serial_tid = (int)W[S::W_STID];
+    MPC_PHASE
+    if (tid == serial_tid) {
+        if (BACKWARD) {
+            double pv[NX];
+            for (int i = 0; i < NX; i++) {
+                pv[i] = sm[N * S::STRIDE + S::GT + NU + i];
+                sm[N * S::STRIDE + S::PV + i] = pv[i];
+            }
+            for (int k = N - 1; k >= 0; k--) {
+                double *st = sm + k * S::STRIDE;
+                const double *stn = st + S::STRIDE;
+                double q[NX], y[NU];
+                for (int l = 0; l < NX; l++) q[l] = pv[l] + stn[S::PC + l];
+                for (int i = 0; i < NU; i++) {
+                    double acc = st[S::GT + i];
+                    for (int l = 0; l < NX; l++) acc += st[S::BB + l * NU + i] * q[l];
+                    for (int c = 0; c < i; c++) acc -= st[S::LUU + tri(i, c)] * y[c];
+                    y[i] = acc * st[S::LUU + tri(i, i)];
+                    st[S::YV + i] = y[i];
+                }
+                for (int i = 0; i < NX; i++) {
+                    double mx = st[S::GT + NU + i] + q[i];
+                    if (R::eidx(i) >= 0)
+                        for (int l = 0; l < NX; l++) mx += st[S::BE + l * NE + (R::eidx(i) >= 0 ? R::eidx(i) : 0)] * q[l];
+                    for (int c = 0; c < NU; c++) mx -= st[S::LXU + i * NU + c] * y[c];
+                    pv[i] = mx;
+                    st[S::PV + i] = mx;
+                }
+            }
+        }
+        double dx[NX];
+        for (int i = 0; i < NX; i++) {
+            dx[i] = W[S::W_DX0 + i];
+            sm[S::DZN + NU + i] = dx[i];
+        }
+        for (int k = 0; k < N; k++) {
+            double *st = sm + k * S::STRIDE;
+            double *stn = st + S::STRIDE;
+            double w[NU], du[NU], dxn[NX];
+            for (int c = 0; c < NU; c++) {
+                double acc = st[S::YV + c];
+                for (int l = 0; l < NX; l++) acc += st[S::LXU + l * NU + c] * dx[l];
+                w[c] = acc;
+            }
+            for (int c = NU - 1; c >= 0; c--) {  // du = -L_uu^-T w
+                double acc = w[c];
+                for (int r = c + 1; r < NU; r++) acc -= st[S::LUU + tri(r, c)] * du[r];
+                du[c] = acc * st[S::LUU + tri(c, c)];
+            }
+            for (int c = 0; c < NU; c++) {
+                du[c] = du[c];
+                st[S::DZN + c] = -du[c];
+            }
+            for (int i = 0; i < NX; i++) {
+                double acc = st[S::C + i] + dx[i];
+                for (int c = 0; c < NU; c++) acc -= st[S::BB + i * NU + c] * du[c];
+                for (int c = 0; c < NE; c++) acc += st[S::BE + i * NE + c] * dx[R::ecol(c)];
+                dxn[i] = acc;
+                stn[S::DZN + NU + i] = acc;
+            }
+            for (int i = 0; i < NX; i++) dx[i] = dxn[i];
+        }
+    }
+    MPC_PHASE_END
+    MPC_PHASE
+    for (int it = tid; it < N * NX; it += NT) {
+        const int k = 1 + it / NX, i = it % NX;
+        double *st = sm + k * S::STRIDE;
+        double acc = st[S::PV + i];
+        for (int mm = 0; mm < NX; mm++) acc += st[S::P + trisym(i, mm)] * st[S::DZN + NU + mm];
+        st[S::PIN + i] = acc;
+    }
+    MPC_PHASE_END
+}
+
 // Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PIN.
 template <class CFG>
 MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
@@ -1385,7 +1572,7 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
                         for (int l = 0; l < NX; l++) rg += st[S::BB + l * NU + i] * stn[S::DPI + l];
                     } else {
                         rg += stn[S::DPI + i - NU];
-                        const int ce = (i - NU == 2) ? 0 : ((i - NU == 3) ? 1 : -1);
+                        const int ce = RicIdx<CFG>::eidx(i - NU);
                         if (ce >= 0) {
 #pragma unroll
                             for (int l = 0; l < NX; l++) rg += st[S::BE + l * S::NE + ce] * stn[S::DPI + l];
@@ -1482,6 +1669,7 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
 #pragma unroll
                     for (int u = 0; u < NU; u++) acc += st[S::BB + r * NU + u] * st[S::DZ + u];
                     acc += st[S::DZ + NU + r] + st[S::BE + r * S::NE] * st[S::DZ + NU + 2] + st[S::BE + r * S::NE + 1] * st[S::DZ + NU + 3];
+                    if (S::NE > 2) acc += st[S::BE + r * S::NE + (S::NE > 2 ? 2 : 0)] * st[S::DZ + NU + 4];
                     upd_max(re, fabs(acc));
                 }
             }
@@ -1690,15 +1878,20 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
         if (rs < L.qp_tol && re < L.qp_tol && ri < L.qp_tol && rc < L.qp_tol) { status = 0; break; }
         if (iter >= L.qp_iter_max) { status = 2; break; }
 
+        if constexpr (CFG::BICYCLE) {
+            riccati_factor_dense<CFG>(sm);  // dense sweeps (nu = 3, three non-identity columns of A)
+        } else {
 #if defined(MPC_RICCATI_LANES)
-        riccati_factor_lanes<CFG>(sm);  // measured alternative: same throughput, 5 % more solo latency
+            riccati_factor_lanes<CFG>(sm);  // measured alternative: same throughput, 5 % more solo latency
 #elif defined(__CUDACC__) && !defined(MPC_RICCATI_SERIAL)
-        riccati_factor_mma<CFG>(sm);    // FP64 tensor-core products, one warp (+ backward sweep of the predictor rhs)
+            riccati_factor_mma<CFG>(sm);    // FP64 tensor-core products, one warp (+ backward sweep of the predictor rhs)
 #else
-        riccati_factor<CFG>(sm);        // + backward sweep of the predictor right-hand side
+            riccati_factor<CFG>(sm);        // + backward sweep of the predictor right-hand side
 #endif
+        }
         MPC_TICK(TK_FACTOR)
-        riccati_solve<CFG>(sm, false);
+        if constexpr (CFG::BICYCLE) riccati_solve_dense<CFG>(sm, false);
+        else riccati_solve<CFG>(sm, false);
         MPC_TICK(TK_SOLVE)
         sigma_mu = 0.0;
         if (nc > 0) {
@@ -1724,7 +1917,8 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
             // ---- PE: corrector gradient and solve ----
             stage_accumulate<CFG, 1>(L, sm, sigma_mu);
             MPC_TICK(TK_ACC1)
-            riccati_solve<CFG>(sm, true);
+            if constexpr (CFG::BICYCLE) riccati_solve_dense<CFG>(sm, true);
+            else riccati_solve<CFG>(sm, true);
             MPC_TICK(TK_SOLVE)
         }
         // ---- PF: step length to the boundary ----
@@ -1894,7 +2088,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
 #pragma unroll
             for (int i = 0; i < NZ; i++) z[i] = st[S::Z + i];
             c = L.dt * stage_cost<CFG>(pa, L, z, 0.0, nullptr, nullptr);
-            unicycle_step<CFG>(L, z, xn, nullptr, nullptr, nullptr);
+            model_step<CFG>(L, z, xn, nullptr, nullptr, nullptr);
 #pragma unroll
             for (int i = 0; i < NX; i++) upd_max(defect, fabs(xn[i] - stn[S::Z + NU + i]));
             if (tid == 0) {

@@ -451,7 +451,15 @@ def config_safe_horizon(N=20, n_scenario=24, n_segments=5) -> ProblemSpec:
     )
 
 
+def config_bicycle(N=20, n_obstacles=4, n_segments=5) -> ProblemSpec:
+    """BASELINE configs[0] as written: BicycleModel2ndOrder (solver_model.py:302-351; inputs a, w, slack; states x, y, psi, v,
+    delta, spline) + MPCBase(a, w, slack, v) + Contouring + Ellipsoid(4).  No shipped generator script of the reference uses this
+    model; the stack is the jackalsimulator `configuration_basic` with the model swapped."""
+    return ProblemSpec("bicycle", model=MODEL_BICYCLE, N=N, n_segments=n_segments, weigh_slack=True, constraints=[(CON_ELLIPSOID, n_obstacles)])
+
+
 CONFIGS = {
+    "cfg0_bicycle": config_bicycle,
     "cfg1": config_basic,
     "cfg2": config_tmpc,
     "cfg3": config_tmpc_decomp,

@@ -417,3 +417,85 @@ def compact_scene(spec: pb.ProblemSpec, batch, n_scenes: int, n_guesses: int):
     guided = np.array([0] + [1] * (G - 1), dtype=np.int32)
     return dict(base_params=base, obstacles=obstacles, obstacle_radius=radius, obstacle_flags=flags, risk=risk, halfspaces=halfspaces,
                 guided=guided, xinit=batch["xinit"].reshape(S, G, nx)[:, 0].copy())
+
+
+def _bicycle_rk4(x, u, dt, steps=3):
+    """BicycleModel2ndOrder.continuous_model (solver_model.py:319-351), states x, y, psi, v, delta, spline; ERK4 x 3."""
+    lr = 2.79 / 2.0
+
+    def f(x):
+        beta = np.arctan(0.5 * np.tan(x[4]))
+        return np.array([x[3] * np.cos(x[2] + beta), x[3] * np.sin(x[2] + beta), x[3] / lr * np.sin(beta), u[0], u[1], x[3]])
+
+    h = dt / steps
+    for _ in range(steps):
+        k1 = f(x)
+        k2 = f(x + 0.5 * h * k1)
+        k3 = f(x + 0.5 * h * k2)
+        k4 = f(x + h * k3)
+        x = x + h / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+    return x
+
+
+def make_bicycle_batch(spec: pb.ProblemSpec, n: int, seed: int = 0):
+    """BASELINE configs[0]: bicycle model, MPCC, ellipsoidal obstacles, one solve per scene (P = 1).  Robot on the reference
+    path with a small lateral / heading / steering offset, warm start = a steering-controlled bicycle roll-out towards the path,
+    obstacles moving alongside the path at >= 2.5 m lateral distance from it (the model is a car: radius 0.325 m disc as in
+    the jackal settings, to keep the parameter semantics of the T-MPC scenes)."""
+    assert spec.model == pb.MODEL_BICYCLE
+    rng = np.random.default_rng(seed)
+    N, nx, nu, nz, npar, dt = spec.N, spec.nx, spec.nu, spec.nz, spec.npar, spec.dt
+    pm = spec.parameter_map()
+    iz = {k: v[1] for k, v in spec.model_map().items()}
+    n_ell = dict(spec.constraints).get(pb.CON_ELLIPSOID, 0)
+    xinit, x0, params = np.zeros((n, nx)), np.zeros((n, N + 1, nz)), np.zeros((n, N, npar))
+    for si in range(n):
+        coef, starts = _fit_path(rng.uniform(0.0, 1.5), spec.n_segments, phase=rng.uniform(0, 2 * np.pi))
+        s0 = rng.uniform(0.5, 1.5)
+        p0, d0 = _path_eval(coef, starts, s0)
+        heading = np.arctan2(d0[1], d0[0])
+        normal = np.array([-np.sin(heading), np.cos(heading)])
+        pos0 = p0 + rng.uniform(-0.3, 0.3) * normal
+        x = np.array([pos0[0], pos0[1], heading + rng.uniform(-0.1, 0.1), rng.uniform(1.0, 2.5), rng.uniform(-0.05, 0.05), s0])
+        xinit[si] = x
+        traj = np.zeros((N + 1, nz))
+        for k in range(N + 1):
+            traj[k, nu:] = x
+            if k == N:
+                break
+            tgt, _ = _path_eval(coef, starts, x[5] + 2.0)
+            err = (np.arctan2(tgt[1] - x[1], tgt[0] - x[0]) - x[2] + np.pi) % (2 * np.pi) - np.pi
+            delta_des = float(np.clip(1.2 * err, -0.4, 0.4))
+            w = float(np.clip((delta_des - x[4]) / dt, -1.2, 1.2))
+            a = float(np.clip((2.0 - x[3]) / (4 * dt), -1.0, 1.0))
+            traj[k, iz["a"]], traj[k, iz["w"]], traj[k, iz["slack"]] = a, w, 0.0
+            x = _bicycle_rk4(x, (a, w), dt)
+        x0[si] = traj
+        par = np.zeros((N, npar))
+        for name in ("acceleration", "angular_velocity", "velocity", "reference_velocity", "contour", "lag", "slack", "terminal_angle", "terminal_contouring"):
+            if name in pm:
+                par[:, pm[name]] = WEIGHTS[name]
+        for i in range(spec.n_segments):
+            for ax, axn in enumerate("xy"):
+                for ci, cn in enumerate("abcd"):
+                    par[:, pm[f"spline_{axn}{i}_{cn}"]] = coef[i, ax, ci]
+            par[:, pm[f"spline{i}_start"]] = starts[i]
+        par[:, pm["ego_disc_radius"]] = ROBOT_RADIUS
+        par[:, pm["ego_disc_0_offset"]] = 0.0
+        t = dt * np.arange(N + 1)
+        for o in range(n_ell):
+            so = rng.uniform(3.0, 18.0)
+            po, do = _path_eval(coef, starts, so)
+            ho = np.arctan2(do[1], do[0])
+            side = 1.0 if rng.random() < 0.5 else -1.0
+            start = po + side * rng.uniform(2.5, 4.0) * np.array([-np.sin(ho), np.cos(ho)])
+            vel = rng.uniform(0.3, 1.0) * np.array([np.cos(ho), np.sin(ho)])
+            pos = start[None, :] + t[:, None] * vel[None, :]
+            pre = f"ellipsoid_obst_{o}_"
+            for k in range(N):
+                vals = (dict(x=pos0[0] + 50, y=pos0[1] + 50, psi=0.0, r=0.1, major=0.0, minor=0.0, chi=1.0) if k == 0 else
+                        dict(x=pos[k, 0], y=pos[k, 1], psi=0.0, r=OBSTACLE_RADIUS, major=0.0, minor=0.0, chi=1.0))
+                for kk, vv in vals.items():
+                    par[k, pm[pre + kk]] = vv
+        params[si] = par
+    return dict(xinit=xinit, x0=x0.reshape(n, -1), params=params.reshape(n, -1))

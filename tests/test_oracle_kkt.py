@@ -132,7 +132,7 @@ def test_every_qp_of_a_solve_is_solved_to_its_optimality_conditions(name):
                     pi, lam = np.zeros((N + 1, nx)), np.zeros((N, max(nh, 1)))
                 else:
                     st = np.zeros((1, oracle.state_size(spec)))
-                    xt_k, ut_k, inf_k = oracle.solve_batch(dataclasses.replace(spec, n_sqp=k_done), xi, x0, par, state=st)
+                    xt_k, ut_k, inf_k = oracle.solve_batch(dataclasses.replace(spec, n_sqp=k_done, res_eq_fail=1e9), xi, x0, par, state=st)
                     assert inf_k[0]["exit_code"] == 1 or inf_k[0]["qp_status"] == 0
                     if not st.any():
                         continue  # demoted intermediate solve: the state was cleared

@@ -211,7 +211,8 @@ def test_later_rti_steps_solve_the_exact_hessian_qp_an_independent_solver_finds(
     N, nx, nu, nz, npar, nh = spec.N, spec.nx, spec.nu, spec.nz, spec.npar, spec.nh
     P = len(b["xinit"])
     state = np.zeros((P, oracle.state_size(spec)))
-    xt_k, ut_k, info_k = oracle.solve_batch(dataclasses.replace(spec, n_sqp=k_done), b["xinit"], b["x0"], b["params"], state=state)
+    # (res_eq_fail lifted for the intermediate run: a demoted solve would clear the multipliers we want to read back)
+    xt_k, ut_k, info_k = oracle.solve_batch(dataclasses.replace(spec, n_sqp=k_done, res_eq_fail=1e9), b["xinit"], b["x0"], b["params"], state=state)
     xt_1, ut_1, info_1 = oracle.solve_batch(dataclasses.replace(spec, n_sqp=k_done + 1), b["xinit"], b["x0"], b["params"])
     lh, uh = map(np.array, spec.constraint_bounds())
     lo, up = np.array(list(d.lower_bound)[:nz]), np.array(list(d.upper_bound)[:nz])
