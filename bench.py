@@ -119,6 +119,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
+    def wait_first_sample(self, timeout=8.0):
+        """nvidia-smi needs up to a few seconds before its first line on an 8-GPU box: do not start the (short) timed region
+        before the sampler is running."""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.lines and time.time() < t_end:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -412,7 +419,9 @@ def main():
     # ---- timed region: device-resident inputs ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.25)
+    sampler.wait_first_sample()
+    for j in range(3):  # the GPU is under load when the timed region starts (and the sampler sees it so)
+        step_device(j)
     launches0 = solver.launches
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
