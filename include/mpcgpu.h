@@ -153,6 +153,13 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
                       const double *params, double *xtraj, double *utraj, mpcgpu_info *info,
                       int *best);
 
+/* As mpcgpu_solve_host with the persistent multipliers of the P solver slots travelling WITH the call (needs
+ * mpcgpu_set_stateful(h, 1)): state[P * mpcgpu_state_size] is uploaded next to the inputs, used, and the updated multipliers
+ * come back next to the outputs -- what a reference Solver's acados memory does across `operator=` and solve()
+ * (acados_solver_interface.cpp:67-77), without the two synchronous round trips of mpcgpu_set_state / mpcgpu_get_state. */
+int mpcgpu_solve_host_stateful(mpcgpu_handle h, int P, const double *xinit, const double *x0, const double *params,
+                               double *state, double *xtraj, double *utraj, mpcgpu_info *info, int *best);
+
 /* Device-buffer path: same arrays already resident in HBM; asynchronous on `stream`
  * (a cudaStream_t passed as void*; NULL = default stream).  The call selects the handle's device.  It uses the
  * handle's scratch buffers (transposed parameters, persistent multipliers, timing events): ONE solve call may be in

@@ -20,7 +20,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 # every symbol include/mpcgpu.h declares
 EXPORTED_SYMBOLS = [
     "mpcgpu_version", "mpcgpu_strerror", "mpcgpu_device_count", "mpcgpu_problem_supported", "mpcgpu_create", "mpcgpu_destroy", "mpcgpu_describe",
-    "mpcgpu_solve_host", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_solve_tmpc_scene_host", "mpcgpu_get_packed_params", "mpcgpu_set_group", "mpcgpu_set_timeout",
+    "mpcgpu_solve_host", "mpcgpu_solve_host_stateful", "mpcgpu_solve_device", "mpcgpu_solve_tmpc_host", "mpcgpu_solve_tmpc_scene_host", "mpcgpu_get_packed_params", "mpcgpu_set_group", "mpcgpu_set_timeout",
     "mpcgpu_set_stateful", "mpcgpu_state_size", "mpcgpu_reset_state", "mpcgpu_get_state", "mpcgpu_set_state", "mpcgpu_host_alloc", "mpcgpu_host_free", "mpcgpu_launch_count",
     "mpcgpu_set_timing", "mpcgpu_kernel_ms", "mpcgpu_eval_stage", "mpcgpu_measure_fp64_gflops",
 ]
@@ -48,6 +48,7 @@ def load_library(path: str | None = None):
     lib.mpcgpu_destroy.argtypes = [ctypes.c_void_p]
     lib.mpcgpu_describe.argtypes = [ctypes.c_void_p, ctypes.POINTER(ProblemDesc), _ip, _ip]
     lib.mpcgpu_solve_host.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, ctypes.POINTER(SolveInfo), _ip]
+    lib.mpcgpu_solve_host_stateful.argtypes = [ctypes.c_void_p, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, _dp, ctypes.POINTER(SolveInfo), _ip]
     lib.mpcgpu_solve_device.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 8
     lib.mpcgpu_solve_tmpc_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, _ip, ctypes.c_double, _dp, _dp,
                                            ctypes.POINTER(SolveInfo), _ip]

@@ -611,10 +611,11 @@ int mpcgpu_solve_device(mpcgpu_handle h, int P, const double *d_xinit, const dou
     return MPCGPU_OK;
 }
 
-int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double *x0, const double *params, double *xtraj,
-                      double *utraj, mpcgpu_info *info, int *best) {
+static int solve_host_impl(mpcgpu_handle h, int P, const double *xinit, const double *x0, const double *params, double *state, double *xtraj,
+                           double *utraj, mpcgpu_info *info, int *best) {
     if (!h || P <= 0 || !xinit || !x0 || !params || !xtraj || !utraj || !info) return MPCGPU_ERR_ARG;
     if (P > h->max_batch) return MPCGPU_ERR_BATCH;
+    if (state && !h->d_state) return MPCGPU_ERR_ARG;  // mpcgpu_set_stateful(h, 1) first
     CUDA_TRY(cudaSetDevice(h->device));
     // Large batches are split into chunks pipelined over three streams (H2D | kernels | D2H) so that the PCIe
     // copies of chunk i+1 / i-1 overlap the solve of chunk i.  Chunks are whole selection groups.
@@ -628,6 +629,7 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
         CUDA_TRY(cudaMemcpyAsync(h->d_xinit + o * h->n_xinit, xinit + o * h->n_xinit, n * h->n_xinit * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
         CUDA_TRY(cudaMemcpyAsync(h->d_x0 + o * h->n_x0, x0 + o * h->n_x0, n * h->n_x0 * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
         CUDA_TRY(cudaMemcpyAsync(h->d_params + o * h->n_params, params + o * h->n_params, n * h->n_params * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        if (state) CUDA_TRY(cudaMemcpyAsync(h->d_state + o * h->n_state, state + o * h->n_state, n * h->n_state * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
         CUDA_TRY(cudaEventRecord(h->ev_in[c], h->stream_in));
     }
     for (int c = 0; c < n_chunks; c++) {
@@ -643,6 +645,7 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
         CUDA_TRY(cudaMemcpyAsync(xtraj + o * h->n_xtraj, h->d_xtraj + o * h->n_xtraj, n * h->n_xtraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
         CUDA_TRY(cudaMemcpyAsync(utraj + o * h->n_utraj, h->d_utraj + o * h->n_utraj, n * h->n_utraj * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
         CUDA_TRY(cudaMemcpyAsync(info + o, h->d_info + o, n * sizeof(mpcgpu_info), cudaMemcpyDeviceToHost, h->stream_out));
+        if (state) CUDA_TRY(cudaMemcpyAsync(state + o * h->n_state, h->d_state + o * h->n_state, n * h->n_state * sizeof(double), cudaMemcpyDeviceToHost, h->stream_out));
         if (best) {
             const size_t ng = (n + group - 1) / group;
             CUDA_TRY(cudaMemcpyAsync(best + o / group, h->d_best + o / group, ng * sizeof(int), cudaMemcpyDeviceToHost, h->stream_out));
@@ -656,6 +659,17 @@ int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double 
         h->ms_n += 1;
     }
     return MPCGPU_OK;
+}
+
+int mpcgpu_solve_host(mpcgpu_handle h, int P, const double *xinit, const double *x0, const double *params, double *xtraj,
+                      double *utraj, mpcgpu_info *info, int *best) {
+    return solve_host_impl(h, P, xinit, x0, params, nullptr, xtraj, utraj, info, best);
+}
+
+int mpcgpu_solve_host_stateful(mpcgpu_handle h, int P, const double *xinit, const double *x0, const double *params, double *state,
+                               double *xtraj, double *utraj, mpcgpu_info *info, int *best) {
+    if (!state) return MPCGPU_ERR_ARG;
+    return solve_host_impl(h, P, xinit, x0, params, state, xtraj, utraj, info, best);
 }
 
 int mpcgpu_host_alloc(void **ptr, unsigned long long bytes) {

@@ -160,9 +160,11 @@ struct SL {
     static constexpr int PIN = DZN + NZ;        // Newton target (equality multiplier)
     // MIRROR work space of the CTA-parallel Jacobi: the working copy of the block lives in the T / TINV / CORR rows (dead
     // between QPs) when they hold NZ x NZ doubles, else in an extra area behind the stage image (bicycle with few rows)
+    static constexpr int ZS = PIN + NX;         // one double that is 0.0 for the whole solve (set at load time, never written): the
+                                                // tensor-core sweep points its structurally absent loads here instead of predicating them
     static constexpr int MIR_EXTRA = (3 * NROW >= NZ * NZ) ? 0 : NZ * NZ;
-    static constexpr int MW = MIR_EXTRA ? PIN + NX : T;
-    static constexpr int RAW = PIN + NX + MIR_EXTRA;
+    static constexpr int MW = MIR_EXTRA ? ZS + 1 : T;
+    static constexpr int RAW = ZS + 1 + MIR_EXTRA;
     static constexpr int STRIDE = RAW | 1;      // odd
     // linearisation scratch inside the work area (dead while linearising): partial Hessians.  It must not touch
     // DPI (= pi, read by the dynamics part of the NEXT stage's... of this stage's predecessor)
@@ -1027,6 +1029,11 @@ MPC_DEV double mpc_lds_if(bool p, unsigned addr) {  // p ? load : 0.0  (one pred
     asm("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q ld.shared.f64 %0, [%1];\n}" : "+d"(v) : "r"(addr), "r"((int)p));
     return v;
 }
+MPC_DEV double mpc_sel(bool p, double a, double b) {  // p ? a : b as one select (no divergent branch on lane-dependent p)
+    double r;
+    asm("{\n .reg .pred q;\n setp.ne.s32 q, %3, 0;\n selp.f64 %0, %1, %2, q;\n}" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+    return r;
+}
 MPC_DEV void mpc_sts_if(bool p, unsigned addr, double v) {
     asm volatile("{\n .reg .pred q;\n setp.ne.s32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}" ::"r"(addr), "d"(v), "r"((int)p) : "memory");
 }
@@ -1045,49 +1052,51 @@ MPC_DEV void riccati_factor_mma(double *sm) {
         const unsigned FULL = 0xffffffffu;
         unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
         asm volatile("" : "+r"(sbase));
-        // ---- per-lane tables (loop invariant): byte offsets inside a stage image; absent entries are flagged ----
+        // ---- per-lane tables (loop invariant): byte offsets inside a stage image.  A structurally absent entry points at the
+        // stage's zero slot (S::ZS), so every load of the stage loop is unconditional; stores keep a flag ----
         // slot s <-> column / contraction index a_s = 2q + s;  its x row l_s = a_s - NU
         int f_off[2], c_off[2], h_off[RT][2], gb_off[RT][2], gs_off[RT][2], gd_off[RT][2], p_off[RT][2], lx_off[RT];
-        int flags = 0;          // bit 0/1: f_has[s]; 2/3: c_has[s]
-        int fl[RT][2], fx[RT];  // per (row tile, slot): bits {0: h, 1: gd, 2: gb, 3: gs, 4: p};  per row tile: own L entry is stored
+        int flags = 0;          // bit 2/3: c_has[s] (store of P+ c)
+        int fl[RT][2], fx[RT];  // per (row tile, slot): bit 4: P / pv entry is stored;  per row tile: own L entry is stored
         double f_id[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             const int a = 2 * q + s, l = a - NU;
             const bool lv = (l >= 0 && l < NX);
             // [B A]_{l, g}: B (g < NU), else A = I + E with E stored for its non-zero columns (psi, v)
-            f_off[s] = 0; f_id[s] = 0.0;
+            f_off[s] = S::ZS; f_id[s] = 0.0;
             if (lv && g < NZ) {
-                if (g < NU) { flags |= 1 << s; f_off[s] = S::BB + l * NU + g; }
+                if (g < NU) f_off[s] = S::BB + l * NU + g;
                 else {
                     const int j = g - NU, e = (j == 2) ? 0 : ((j == 3) ? 1 : -1);
                     f_id[s] = (l == j) ? 1.0 : 0.0;
-                    if (e >= 0) { flags |= 1 << s; f_off[s] = S::BE + l * NE + e; }
+                    if (e >= 0) f_off[s] = S::BE + l * NE + e;
                 }
             }
             if (lv) flags |= 4 << s;
-            c_off[s] = S::C + (lv ? l : 0);
+            c_off[s] = lv ? S::C + l : S::ZS;
 #pragma unroll
             for (int rt = 0; rt < RT; rt++) {
                 const int n = 8 * rt + g;
                 int &F = fl[rt][s];
                 F = 0;
-                h_off[rt][s] = gb_off[rt][s] = gs_off[rt][s] = gd_off[rt][s] = p_off[rt][s] = 0;
+                h_off[rt][s] = gb_off[rt][s] = gs_off[rt][s] = gd_off[rt][s] = S::ZS;
+                p_off[rt][s] = 0;
                 if (a < NZ) {
                     if (n < NZ) {
-                        F |= 1; h_off[rt][s] = S::H + trisym(n, a);
-                        if (n == a) { F |= 2; gd_off[rt][s] = S::GD + a; }
+                        h_off[rt][s] = S::H + trisym(n, a);
+                        if (n == a) gd_off[rt][s] = S::GD + a;
                         const int an = (n == CFG::IX) ? 0 : (n == CFG::IY) ? 1 : (n == CFG::IPSI) ? 2 : -1;
                         const int aa = (a == CFG::IX) ? 0 : (a == CFG::IY) ? 1 : (a == CFG::IPSI) ? 2 : -1;
-                        if (an >= 0 && aa >= 0) { F |= 4; gb_off[rt][s] = S::GB + trisym(an, aa); }
+                        if (an >= 0 && aa >= 0) gb_off[rt][s] = S::GB + trisym(an, aa);
                         if (CFG::ANY_SLACK_ROWS) {
-                            if (n == CFG::ISLACK && aa >= 0) { F |= 8; gs_off[rt][s] = S::GS + aa; }
-                            if (a == CFG::ISLACK && an >= 0) { F |= 8; gs_off[rt][s] = S::GS + an; }
-                            if (n == CFG::ISLACK && a == CFG::ISLACK) { F |= 8; gs_off[rt][s] = S::GS + 3; }
+                            if (n == CFG::ISLACK && aa >= 0) gs_off[rt][s] = S::GS + aa;
+                            if (a == CFG::ISLACK && an >= 0) gs_off[rt][s] = S::GS + an;
+                            if (n == CFG::ISLACK && a == CFG::ISLACK) gs_off[rt][s] = S::GS + 3;
                         }
                         if (n >= NU && l >= 0 && l <= n - NU) { F |= 16; p_off[rt][s] = S::P + tri(n - NU, l); }  // lower triangle of P
                     } else if (n == NZ) {
-                        F |= 1; h_off[rt][s] = S::GT + a;
+                        h_off[rt][s] = S::GT + a;
                         if (lv) { F |= 16; p_off[rt][s] = S::PV + l; }
                     }
                 }
@@ -1148,14 +1157,14 @@ MPC_DEV void riccati_factor_mma(double *sm) {
         auto load_stage = [&](const unsigned st) {
 #pragma unroll
             for (int s = 0; s < 2; s++) {
-                fv[s] = mpc_lds_if((flags >> s) & 1, st + f_off[s]);
-                cv[s] = mpc_lds_if((flags >> (2 + s)) & 1, st + c_off[s]);
+                fv[s] = mpc_lds(st + f_off[s]);
+                cv[s] = mpc_lds(st + c_off[s]);
 #pragma unroll
                 for (int rt = 0; rt < RT; rt++) {
-                    raw[rt][s][0] = mpc_lds_if(fl[rt][s] & 1, st + h_off[rt][s]);
-                    raw[rt][s][1] = mpc_lds_if(fl[rt][s] & 2, st + gd_off[rt][s]);
-                    raw[rt][s][2] = mpc_lds_if(fl[rt][s] & 4, st + gb_off[rt][s]);
-                    raw[rt][s][3] = CFG::ANY_SLACK_ROWS ? mpc_lds_if(fl[rt][s] & 8, st + gs_off[rt][s]) : 0.0;
+                    raw[rt][s][0] = mpc_lds(st + h_off[rt][s]);
+                    raw[rt][s][1] = mpc_lds(st + gd_off[rt][s]);
+                    raw[rt][s][2] = mpc_lds(st + gb_off[rt][s]);
+                    raw[rt][s][3] = CFG::ANY_SLACK_ROWS ? mpc_lds(st + gs_off[rt][s]) : 0.0;
                 }
             }
         };
@@ -1199,7 +1208,7 @@ MPC_DEV void riccati_factor_mma(double *sm) {
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 mpc_sts_if(is_vec && ((flags >> (2 + s)) & 1), stn + (S::PC - NU) * 8 + 16 * q + 8 * s, w[VT][s]);
-                w[VT][s] += is_vec ? Pt[VT][s] : 0.0;
+                w[VT][s] += mpc_sel(is_vec, Pt[VT][s], 0.0);
             }
             // GEMM 2: Mt = Wt [B A] + (H + G | gt)
             double m[RT][2];
@@ -1230,7 +1239,7 @@ MPC_DEV void riccati_factor_mma(double *sm) {
             for (int rt = 0; rt < RT; rt++) {
                 const double L0 = t0[rt] * il00;
                 const double L1 = (t1[rt] - L0 * l10) * il11;
-                Lq[rt] = (q == 0) ? L0 : ((q == 1) ? L1 : 0.0);
+                Lq[rt] = mpc_sel(q == 1, L1, mpc_sel(q == 0, L0, 0.0));
                 mpc_sts_if(fx[rt] != 0, st + lx_off[rt], Lq[rt]);
             }
             // GEMM 3: Pt = Mt - L L'

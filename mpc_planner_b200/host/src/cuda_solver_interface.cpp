@@ -98,22 +98,47 @@ void Solver::initializeOneIteration() {  // :121-143
     _iteration_done = false;
 }
 
+namespace {
+// Pinned staging of one batched launch, owned by the lead solver's handle and reused from control step to control step
+// (round 1 heap-allocated five vectors and made two synchronous state round trips per step).
+struct BatchStaging {
+    void *base = nullptr;
+    size_t bytes = 0;
+    double *xinit = nullptr, *x0 = nullptr, *par = nullptr, *mult = nullptr, *xtraj = nullptr, *utraj = nullptr;
+    mpcgpu_info *info = nullptr;
+    void ensure(size_t P, size_t nxi, size_t nx0, size_t np, size_t ns, size_t nxt, size_t nut) {
+        const size_t doubles = P * (nxi + nx0 + np + ns + nxt + nut);
+        const size_t need = doubles * sizeof(double) + P * sizeof(mpcgpu_info);
+        if (need > bytes) {
+            if (base) mpcgpu_host_free(base);
+            base = nullptr;
+            if (mpcgpu_host_alloc(&base, need) != 0) throw std::runtime_error("mpcgpu_host_alloc failed");
+            bytes = need;
+        }
+        double *p = static_cast<double *>(base);
+        xinit = p; p += P * nxi;
+        x0 = p; p += P * nx0;
+        par = p; p += P * np;
+        mult = p; p += P * ns;
+        xtraj = p; p += P * nxt;
+        utraj = p; p += P * nut;
+        info = reinterpret_cast<mpcgpu_info *>(p);
+    }
+    ~BatchStaging() {
+        if (base) mpcgpu_host_free(base);
+    }
+};
+BatchStaging &staging() {
+    static thread_local BatchStaging s;  // a Solver is not re-entrant (SURVEY 8b "Threading"); one staging area per host thread
+    return s;
+}
+}  // namespace
+
 int Solver::solveOneIteration() {  // :145-160
     if (_iteration_done) return _exit_code_one_iter == 1 ? 0 : _exit_code_one_iter;
-    mpcgpu_info info;
-    std::vector<double> xtraj(_output.xtraj.size()), utraj(_output.utraj.size());
-    mpcgpu_handle h = handle(1);
-    if (!persistent_multipliers) std::fill(_nlp_multipliers.begin(), _nlp_multipliers.end(), 0.0);
-    int rc = mpcgpu_set_state(h, 0, 1, _nlp_multipliers.data());
-    // :91,112 the RTI loop stops when the budget is used up; _params.solver_timeout <= 0 (never set) leaves it unbounded
-    if (rc == 0) rc = mpcgpu_set_timeout(h, _params.solver_timeout);
-    if (rc == 0)
-        rc = mpcgpu_solve_host(h, 1, _params.xinit.data(), _loaded_x0.data(), _params.all_parameters.data(), xtraj.data(), utraj.data(),
-                               &info, nullptr);
-    if (rc == 0) rc = mpcgpu_get_state(h, 0, 1, _nlp_multipliers.data());
-    if (rc != 0) throw std::runtime_error(std::string("mpcgpu_solve_host: ") + mpcgpu_strerror(rc));
-    storeResult(xtraj.data(), utraj.data(), info);
-    _iteration_done = true;
+    std::vector<Solver *> one{this};
+    std::vector<int> codes;
+    solveBatch(one, codes);
     return _exit_code_one_iter == 1 ? 0 : _exit_code_one_iter;
 }
 
@@ -125,36 +150,33 @@ int Solver::solveBatch(const std::vector<Solver *> &solvers, std::vector<int> &e
     if (P == 0) return -1;
     Solver *lead = solvers[0];
     const size_t nxi = lead->_params.xinit.size(), nx0 = lead->_params.x0.size(), np = lead->_params.all_parameters.size();
-    const size_t nxt = lead->_output.xtraj.size(), nut = lead->_output.utraj.size();
-    std::vector<double> xinit(P * nxi), x0(P * nx0), par(P * np), xtraj(P * nxt), utraj(P * nut);
-    std::vector<mpcgpu_info> info(P);
+    const size_t nxt = lead->_output.xtraj.size(), nut = lead->_output.utraj.size(), ns = lead->_nlp_multipliers.size();
+    mpcgpu_handle h = lead->handle(P);
+    BatchStaging &st = staging();
+    st.ensure(P, nxi, nx0, np, ns, nxt, nut);
     for (int i = 0; i < P; i++) {
-        std::copy(solvers[i]->_params.xinit.begin(), solvers[i]->_params.xinit.end(), xinit.begin() + i * nxi);
-        std::copy(solvers[i]->_loaded_x0.begin(), solvers[i]->_loaded_x0.end(), x0.begin() + i * nx0);
-        std::copy(solvers[i]->_params.all_parameters.begin(), solvers[i]->_params.all_parameters.end(), par.begin() + i * np);
+        std::copy(solvers[i]->_params.xinit.begin(), solvers[i]->_params.xinit.end(), st.xinit + i * nxi);
+        std::copy(solvers[i]->_loaded_x0.begin(), solvers[i]->_loaded_x0.end(), st.x0 + i * nx0);
+        std::copy(solvers[i]->_params.all_parameters.begin(), solvers[i]->_params.all_parameters.end(), st.par + i * np);
+        // each Solver owns its multipliers (slot i of the launch <- solvers[i]'s, and back): they travel with the call
+        if (persistent_multipliers) std::copy(solvers[i]->_nlp_multipliers.begin(), solvers[i]->_nlp_multipliers.end(), st.mult + i * ns);
+        else std::fill(st.mult + i * ns, st.mult + (i + 1) * ns, 0.0);
     }
     int best = -1;
-    // each Solver owns its multipliers (slot i of the launch <- solvers[i]'s, and back)
-    const size_t ns = lead->_nlp_multipliers.size();
-    std::vector<double> mult(P * ns, 0.0);
-    if (persistent_multipliers)
-        for (int i = 0; i < P; i++) std::copy(solvers[i]->_nlp_multipliers.begin(), solvers[i]->_nlp_multipliers.end(), mult.begin() + i * ns);
-    mpcgpu_handle h = lead->handle(P);
-    int rc = mpcgpu_set_state(h, 0, P, mult.data());
+    int rc = 0;
     {   // guidance_constraints.cpp:333 gives every local planner the same budget; one launch: the smallest, unbounded if any is unset
         double tmo = solvers[0]->_params.solver_timeout;
         for (const Solver *sv : solvers) tmo = (sv->_params.solver_timeout <= 0.0 || tmo <= 0.0) ? 0.0 : std::min(tmo, sv->_params.solver_timeout);
-        if (rc == 0) rc = mpcgpu_set_timeout(h, tmo);
+        rc = mpcgpu_set_timeout(h, tmo);
     }
-    if (rc == 0) rc = mpcgpu_solve_host(h, P, xinit.data(), x0.data(), par.data(), xtraj.data(), utraj.data(), info.data(), &best);
-    if (rc == 0) rc = mpcgpu_get_state(h, 0, P, mult.data());
-    if (rc != 0) throw std::runtime_error(std::string("mpcgpu_solve_host: ") + mpcgpu_strerror(rc));
+    if (rc == 0) rc = mpcgpu_solve_host_stateful(h, P, st.xinit, st.x0, st.par, st.mult, st.xtraj, st.utraj, st.info, &best);
+    if (rc != 0) throw std::runtime_error(std::string("mpcgpu_solve_host_stateful: ") + mpcgpu_strerror(rc));
     for (int i = 0; i < P; i++) {
-        std::copy(mult.begin() + i * ns, mult.begin() + (i + 1) * ns, solvers[i]->_nlp_multipliers.begin());
+        std::copy(st.mult + i * ns, st.mult + (i + 1) * ns, solvers[i]->_nlp_multipliers.begin());
         solvers[i]->_info = Info();
-        solvers[i]->storeResult(xtraj.data() + i * nxt, utraj.data() + i * nut, info[i]);
+        solvers[i]->storeResult(st.xtraj + i * nxt, st.utraj + i * nut, st.info[i]);
         solvers[i]->_iteration_done = true;
-        exit_codes[i] = info[i].exit_code;
+        exit_codes[i] = st.info[i].exit_code;
     }
     return best;
 }
