@@ -996,21 +996,6 @@ MPC_DEV void riccati_factor_lanes(double *sm) {
 // Device only: the host emulation (tests/emu) runs the single-thread sweep, to which this one is algebraically identical.
 // ---------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-// Two independent reciprocal square roots of normal positive numbers, their instruction streams interleaved.  Arithmetic of
-// CUDA's rsqrt(double) fast path: MUFU.RSQ64H seed y (upper word), e = 1 - x y^2, r = y + (y e)(1/2 + 3/8 e) -- bitwise the
-// same result for normal arguments; zero / negative / non-finite arguments (an indefinite input block: the QP has failed)
-// give NaN where rsqrt() may give inf, and every caller multiplies the result by finite terms that turn inf into NaN too.
-MPC_DEV void mpc_rsqrt_pair(const double x0, const double x1, double &r0, double &r1) {
-    double y0, y1;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x0));
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y1) : "d"(x1));
-    const double e0 = fma(x0, -(y0 * y0), 1.0), e1 = fma(x1, -(y1 * y1), 1.0);
-    const double p0 = fma(e0, 0.375, 0.5), p1 = fma(e1, 0.375, 0.5);
-    const double t0 = y0 * e0, t1 = y1 * e1;
-    r0 = fma(p0, t0, y0);
-    r1 = fma(p1, t1, y1);
-}
-
 MPC_DEV void mpc_dmma(double &d0, double &d1, const double a, const double b, const double c0, const double c1) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
         : "=d"(d0), "=d"(d1)
