@@ -36,7 +36,7 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, output=None, registry_header=None, stage_header=None):
+def build(force=False, verbose=False, output=None, registry_header=None, stage_header=None, extra_flags=()):
     """Compile the library.  With `registry_header` (a file emitted by generate.generate_cuda_registry) the kernels
     are instantiated for that module stack only and the result is written to `output`."""
     out = output or LIB
@@ -48,6 +48,7 @@ def build(force=False, verbose=False, output=None, registry_header=None, stage_h
         extra = ["-DMPCGPU_GENERATED_REGISTRY=\"%s\"" % os.path.abspath(registry_header)]
     if stage_header is not None:  # stage functions emitted by codegen.py (MPCGPU_OBJ_GENERATED / MPCGPU_CON_GENERATED)
         extra += ["-DMPCGPU_GENERATED_STAGE=\"%s\"" % os.path.abspath(stage_header)]
+    extra += list(extra_flags)  # development variants (scripts/): -DMPC_NT_OVERRIDE=..., -DMPC_MIN_CTAS=...
     cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-I" + os.path.join(ROOT, "include"), "-o", out] + [
         os.path.join(CSRC, s) for s in SOURCES
     ]

@@ -238,6 +238,9 @@ __global__ void pack_scene_kernel(const double *__restrict__ base, const double 
 
 template <class CFG>
 constexpr int sqp_min_ctas() {
+#if defined(MPC_MIN_CTAS)  // development builds (scripts/residency_sweep.py): fixed register budget
+    return MPC_MIN_CTAS;
+#endif
     return (233472 / (int)(SL<CFG>::TOTAL * sizeof(double) + 1024)) >= 4   ? 4
            : (233472 / (int)(SL<CFG>::TOTAL * sizeof(double) + 1024)) >= 1 ? (233472 / (int)(SL<CFG>::TOTAL * sizeof(double) + 1024))
                                                                             : 1;
@@ -340,6 +343,12 @@ cudaError_t prepare_cfg(int smem_bytes) {
 template <class CFG>
 void launch_sqp_cfg(const Layout &L, int P, const double *xinit, const double *x0, const double *pt, double *xtraj, double *utraj,
                     mpcgpu_info *info, unsigned int *sm_slots, double *state, int smem, cudaStream_t s) {
+#if defined(MPC_DEV_KNOBS)  // development builds: MPCGPU_SMEM_PAD bytes of unused dynamic shared memory lower the residency
+    if (const char *e = getenv("MPCGPU_SMEM_PAD")) {
+        smem += atoi(e);
+        cudaFuncSetAttribute(sqp_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
+#endif
     sqp_kernel<CFG><<<P, MPC_NT, smem, s>>>(L, P, xinit, x0, pt, xtraj, utraj, info, sm_slots, state);
 }
 template <class CFG>

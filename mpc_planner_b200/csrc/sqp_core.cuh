@@ -434,18 +434,17 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
     constexpr int N = CFG::N, NZ = CFG::NZ, NT = MPC_NT;
     constexpr int M = (NZ + 1) & ~1, G = M / 2;  // rounds use M indices (index NZ is a dummy when NZ is odd); G pairs per round
     constexpr int CS = S::WK + NZ * NZ;          // (c, s) of the current round: 2 G doubles
-    static_assert(N * G <= NT, "one thread per (stage, pair of the round)");
     static_assert(S::DZN - S::WK >= NZ * NZ + 2 * G, "MIRROR work space");
     const double eps = L.reg_epsilon;
     // copy the packed block into the work space, V = I (rows split over the G threads of a stage)
     MPC_PHASE
-    if (tid < N * G) {
-        double *st = sm + (tid / G) * S::STRIDE;
+    for (int item = tid; item < N * G; item += NT) {  // item = (stage, pair of the round)
+        double *st = sm + (item / G) * S::STRIDE;
 #if !defined(__CUDACC__) && defined(MPC_EMU_TRACE)
-        if (st[S::DZN] == 2.0 && tid % G == 0) g_mirror_general++;
+        if (st[S::DZN] == 2.0 && item % G == 0) g_mirror_general++;
 #endif
         if (st[S::DZN] == 2.0)
-            for (int i = tid % G; i < NZ; i += G)
+            for (int i = item % G; i < NZ; i += G)
                 for (int j = 0; j < NZ; j++) {
                     st[S::MW + i * NZ + j] = st[S::H + trisym(i, j)];
                     st[S::WK + i * NZ + j] = (i == j) ? 1.0 : 0.0;
@@ -455,8 +454,9 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
     for (int sweep = 0; sweep < 30; sweep++) {
         int active = 0;
         MPC_PHASE
-        if (tid < N * G && tid % G == 0) {  // convergence of each flagged stage (same rule as the register Jacobi)
-            double *st = sm + (tid / G) * S::STRIDE;
+        for (int item = tid; item < N * G; item += NT) {  // convergence of each flagged stage (same rule as the register Jacobi)
+            if (item % G != 0) continue;
+            double *st = sm + (item / G) * S::STRIDE;
             if (st[S::DZN] == 2.0) {
                 const double *Mw = st + S::MW;
                 double offd = 0.0, diag = 0.0;
@@ -472,9 +472,9 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
         if (!active) break;
         for (int r = 0; r < M - 1; r++) {
             MPC_PHASE
-            if (tid < N * G) {  // rotation of the own pair; column updates of A and V
-                double *st = sm + (tid / G) * S::STRIDE;
-                const int j = tid % G;
+            for (int item = tid; item < N * G; item += NT) {  // rotation of the own pair; column updates of A and V
+                double *st = sm + (item / G) * S::STRIDE;
+                const int j = item % G;
                 int p, q;
                 tournament_pair(M, r, j, p, q);
                 double c = 1.0, sn = 0.0;
@@ -498,9 +498,9 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
             }
             MPC_PHASE_END
             MPC_PHASE
-            if (tid < N * G) {  // row updates
-                double *st = sm + (tid / G) * S::STRIDE;
-                const int j = tid % G;
+            for (int item = tid; item < N * G; item += NT) {  // row updates
+                double *st = sm + (item / G) * S::STRIDE;
+                const int j = item % G;
                 int p, q;
                 tournament_pair(M, r, j, p, q);
                 const double c = st[CS + 2 * j], sn = st[CS + 2 * j + 1];
@@ -518,8 +518,8 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
     }
     // rebuild V f(D) V' into the packed block (rows split over the G threads): eigenvalues e -> eps if |e| <= eps, else |e|
     MPC_PHASE
-    if (tid < N * G) {
-        double *st = sm + (tid / G) * S::STRIDE;
+    for (int item = tid; item < N * G; item += NT) {
+        double *st = sm + (item / G) * S::STRIDE;
         if (st[S::DZN] >= 2.0) {
             const double *Mw = st + S::MW, *Vw = st + S::WK;
             double e[NZ];
@@ -529,7 +529,7 @@ MPC_DEV void mirror_general_cta(const Layout &L, double *sm) {
                 else if (l < 0.0) l = -l;
                 e[k] = l;
             }
-            for (int i = tid % G; i < NZ; i += G)
+            for (int i = item % G; i < NZ; i += G)
                 for (int j = 0; j <= i; j++) {
                     double acc = 0.0;
                     for (int k = 0; k < NZ; k++) acc += Vw[i * NZ + k] * e[k] * Vw[j * NZ + k];
