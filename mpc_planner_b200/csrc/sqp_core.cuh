@@ -156,11 +156,10 @@ struct SL {
     static constexpr int DPI = DZ + NZ;         // equality multipliers: QP iterate during the IPM, NLP multiplier pi_k
                                                 // of the equation defining x_k between QPs (read by the linearisation)
     static constexpr int PI = DPI;
-    static constexpr int DZN = DPI + NX;        // Newton target (primal)
-    static constexpr int PIN = DZN + NZ;        // Newton target (equality multiplier)
+    static constexpr int DZN = DPI + NX;        // Newton target (primal); the multiplier target P dx + pv is formed on the fly
     // MIRROR work space of the CTA-parallel Jacobi: the working copy of the block lives in the T / TINV / CORR rows (dead
     // between QPs) when they hold NZ x NZ doubles, else in an extra area behind the stage image (bicycle with few rows)
-    static constexpr int ZS = PIN + NX;         // one double that is 0.0 for the whole solve (set at load time, never written): the
+    static constexpr int ZS = DZN + NZ;         // one double that is 0.0 for the whole solve (set at load time, never written): the
                                                 // tensor-core sweep points its structurally absent loads here instead of predicating them
     static constexpr int MIR_EXTRA = (3 * NROW >= NZ * NZ) ? 0 : NZ * NZ;
     static constexpr int MW = MIR_EXTRA ? ZS + 1 : T;
@@ -320,15 +319,22 @@ MPC_HD void linearize_part(const PA &pa, const Layout &L, double *st, const doub
         const int q = part - 2;
         double Hx[6] = {0, 0, 0, 0, 0, 0};
         if (NH > 0 && k >= 1) {
-            // rows [lo, hi) of h; raw h and dh/d(x,y,psi) go straight to shared memory
-            const int lo = (NH * q) / 4, hi = (NH * (q + 1)) / 4;
-            stage_constraints<CFG, true>(pa, L, z, st + S::RH, st + S::JR, st + S::LAM + 2 * NZ, Hx, lo, hi);
-            for (int j = lo; j < hi; j++) {  // fold the bound side: row value s (h - bound) >= 0, gradient s dh
-                const double sgn = row_sign_of<CFG>(j);
-                st[S::RH + j] = sgn * (st[S::RH + j] - row_bound_of<CFG>(j)) + L.qp_relax;
-                st[S::JR + 3 * j] *= sgn;
-                st[S::JR + 3 * j + 1] *= sgn;
-                st[S::JR + 3 * j + 2] *= sgn;
+            // a quarter of the rows of h; raw h and dh/d(x,y,psi) go straight to shared memory.  Hand-written stacks: quarter q of
+            // EVERY constraint block (each thread gets its share of the expensive ellipsoid / Gaussian rows); emitted stage
+            // functions (codegen.py) take a contiguous row range
+            constexpr bool GEN = (CFG::KIND0 == MPCGPU_CON_GENERATED);
+            if (GEN) stage_constraints<CFG, true>(pa, L, z, st + S::RH, st + S::JR, st + S::LAM + 2 * NZ, Hx, (NH * q) / 4, (NH * (q + 1)) / 4);
+            else stage_constraints<CFG, true>(pa, L, z, st + S::RH, st + S::JR, st + S::LAM + 2 * NZ, Hx, 0, NH, q, 4);
+#pragma unroll
+            for (int m = 0; m < (GEN ? 1 : 3); m++) {
+                const int n = GEN ? NH : CFG::count(m), row0 = GEN ? 0 : CFG::offset(m);
+                for (int j = row0 + (n * q) / 4; j < row0 + (n * (q + 1)) / 4; j++) {  // fold the bound side: row value s (h - bound) >= 0, gradient s dh
+                    const double sgn = row_sign_of<CFG>(j);
+                    st[S::RH + j] = sgn * (st[S::RH + j] - row_bound_of<CFG>(j)) + L.qp_relax;
+                    st[S::JR + 3 * j] *= sgn;
+                    st[S::JR + 3 * j + 1] *= sgn;
+                    st[S::JR + 3 * j + 2] *= sgn;
+                }
             }
         }
 #pragma unroll
@@ -1225,7 +1231,16 @@ MPC_DEV void riccati_factor_mma(double *sm) {
                 const double L0 = t0[rt] * il00;
                 const double L1 = (t1[rt] - L0 * l10) * il11;
                 Lq[rt] = mpc_sel(q == 1, L1, mpc_sel(q == 0, L0, 0.0));
+                // what the vector sweeps read (riccati_solve_mma): x rows  Kt = L_xu L_uu^-1  (the feedback gain, transposed:
+                // du = f - Kt' dx), vector row  y = L_uu^-1 m_u
+#if !defined(MPC_SOLVE_MMA)  // the single-thread sweeps (riccati_solve) read L_xu
                 mpc_sts_if(fx[rt] != 0, st + lx_off[rt], Lq[rt]);
+#else
+                const double K1 = L1 * il11;
+                const double K0 = (L0 - K1 * l10) * il00;
+                const bool yrow = (rt == VT) && is_vec;
+                mpc_sts_if(fx[rt] != 0, st + lx_off[rt], mpc_sel(yrow, Lq[rt], mpc_sel(q == 1, K1, K0)));
+#endif
             }
             // GEMM 3: Pt = Mt - L L'
 #pragma unroll
@@ -1234,6 +1249,207 @@ MPC_DEV void riccati_factor_mma(double *sm) {
 #pragma unroll
                 for (int s = 0; s < 2; s++) mpc_sts_if(fl[rt][s] & 16, st + p_off[rt][s], Pt[rt][s]);
             }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vector sweeps on the FP64 tensor-core path (one warp; device only, pairs with riccati_factor_mma) -- a MEASURED
+// ALTERNATIVE kept under -DMPC_SOLVE_MMA, not the shipped path: parity with the oracle 5.5e-11, but 15 % slower than the
+// single-thread sweeps (bench batch 7.57 vs 6.58 ms, one control step 0.799 vs 0.680 ms).
+//
+// A lone thread runs the shipped sweeps (riccati_solve): 19 % of the kernel's warp instructions at 1 of 32 lanes, a quarter
+// of a solve's time under load, ~170 cycles per stage and sweep.  With the feedback gain stored as Kt = L_xu L_uu^-1
+// (du = f - Kt' dx with f = -L_uu^-T y) both sweeps are ONE vector-matrix product per stage with the closed-loop
+// matrix Acl = A - B Kt':
+//   backward   [pv_k | m_u,k]   = [gt_x | 0] + [q_k+1 | gt_u,k] Mb_k ,   q_k = pv_k + P_k c_k-1 ,   y_k = L_uu^-1 m_u,k
+//              Mb = [ Acl   B ]      (pv = gt_x - Kt gt_u + Acl' q:  the recursion  m = gt + [B A]' q,  y = L_uu^-1 m_u,
+//                   [ -Kt'  I ]       pv = m_x - L_xu y  of riccati_solve with y eliminated;  m_u = gt_u + B' q)
+//   forward    [dx_k+1 | du_k]  = [c_k | 0] + [dx_k | f_k] Mf_k
+//              Mf = [ Acl'  -Kt ]
+//                   [ B'     I  ]
+// The row vector is row 0 of an m8n8k4 tile (columns: NX states, then the NU inputs); with the contraction enumerated
+// "even / odd" the two C registers of a lane are the A fragments of the next product (see riccati_factor_mma): the chain
+// per stage is two dependent DMMA (+ one add in the backward sweep).  Every lane forms its two matrix entries
+// (2q + s, g) of the stage from [B A], Kt through per-lane offset tables (absent operands read the stage's zero slot), one
+// stage ahead of the chain.  Same algebra as the serial sweeps up to rounding.  Why it loses: the chain is short (two DMMA),
+// but a warp issues in order and forming the entries on the fly costs ~17 LDS + 6 FMA per stage on top of the products --
+// ~50 warp instructions per stage and sweep against the lone thread's ~70 cheap ones, ~310 cycles against ~170.  Storing the
+// closed-loop matrix (25 doubles per stage) would fix that; the stage image has 4 doubles left.
+// ---------------------------------------------------------------------------------------------
+MPC_DEV double mpc_lds_v(unsigned addr) {  // load of data written earlier in the same function by another lane
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <class CFG>
+MPC_DEV void riccati_solve_mma(double *sm, bool BACKWARD) {
+    typedef SL<CFG> S;
+    typedef RicIdx<CFG> R;
+    constexpr int N = CFG::N, NZ = CFG::NZ, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
+    static_assert(NU == 2 && NZ <= 8, "one tile: NX state columns + NU input columns");
+    constexpr int SB = S::STRIDE * 8;  // bytes per stage image
+    const int serial_tid = (int)sm[S::W_BASE + S::W_STID];
+    if (((int)threadIdx.x & ~31) == serial_tid) {
+        const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+        const unsigned FULL = 0xffffffffu;
+        unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+        asm volatile("" : "+r"(sbase));
+        // row-vector bookkeeping of the own two slots (columns 2q, 2q + 1 of row g; only row 0 carries data)
+        int xcol[2], ins[2];  // byte offset of the column inside an NX-vector (-1: not a state column of row 0); 1 / 2: input column 0 / 1
+#pragma unroll
+        for (int s2 = 0; s2 < 2; s2++) {
+            const int col = 2 * q + s2;
+            xcol[s2] = (g == 0 && col < NX) ? 8 * col : -1;
+            ins[s2] = (g == 0 && col >= NX && col < NZ) ? 1 + (col - NX) : 0;
+            mpc_opaque(xcol[s2]);
+            mpc_opaque(ins[s2]);
+        }
+        // matrix entry (i = 2q + s, n = g) of the stage:  id + sgn * ld(eo) - ld(b0) ld(k0) - ld(b1) ld(k1)
+        auto tables = [&](const bool fwd, int (&eo)[2], int (&b0)[2], int (&k0)[2], int (&b1)[2], int (&k1)[2], double (&idv)[2], double (&sg)[2]) {
+#pragma unroll
+            for (int s2 = 0; s2 < 2; s2++) {
+                const int i = 2 * q + s2, n = g;
+                eo[s2] = b0[s2] = k0[s2] = b1[s2] = k1[s2] = S::ZS;
+                idv[s2] = 0.0;
+                sg[s2] = 1.0;
+                if (i < NX && n < NX) {
+                    const int r = fwd ? n : i, c = fwd ? i : n;  // Acl[r][c]; the forward sweep multiplies by Acl'
+                    idv[s2] = (r == c) ? 1.0 : 0.0;
+                    const int e = R::eidx(c);
+                    if (e >= 0) eo[s2] = S::BE + r * NE + e;
+                    b0[s2] = S::BB + r * NU;
+                    b1[s2] = S::BB + r * NU + 1;
+                    k0[s2] = S::LXU + c * NU;
+                    k1[s2] = S::LXU + c * NU + 1;
+                } else if (i >= NX && i < NZ && n < NX) {
+                    if (fwd) eo[s2] = S::BB + n * NU + (i - NX);
+                    else { eo[s2] = S::LXU + n * NU + (i - NX); sg[s2] = -1.0; }
+                } else if (i < NX && n >= NX && n < NZ) {
+                    if (fwd) { eo[s2] = S::LXU + i * NU + (n - NX); sg[s2] = -1.0; }
+                    else eo[s2] = S::BB + i * NU + (n - NX);
+                } else if (i >= NX && i < NZ && n >= NX && n < NZ) {
+                    idv[s2] = (i == n) ? 1.0 : 0.0;
+                }
+                eo[s2] *= 8; b0[s2] *= 8; k0[s2] *= 8; b1[s2] *= 8; k1[s2] *= 8;
+                mpc_opaque(eo[s2]); mpc_opaque(b0[s2]); mpc_opaque(k0[s2]); mpc_opaque(b1[s2]); mpc_opaque(k1[s2]);
+            }
+        };
+        int eo[2], b0[2], k0[2], b1[2], k1[2];
+        double idv[2], sg[2];
+        double x[2];
+        if (BACKWARD) {
+            tables(false, eo, b0, k0, b1, k1, idv, sg);
+            // q_N = gt_N + P_N c_N-1 (pv_N = gt_N), input columns: gt_u of stage N - 1
+            {
+                const unsigned stN = sbase + N * SB, stp = stN - SB;
+                const double u0 = mpc_lds(stp + S::GT * 8), u1 = mpc_lds(stp + S::GT * 8 + 8);
+#pragma unroll
+                for (int s2 = 0; s2 < 2; s2++) {
+                    const bool xc = xcol[s2] >= 0;
+                    const double gtn = mpc_lds(xc ? stN + (S::GT + NU) * 8 + xcol[s2] : stN + S::ZS * 8);
+                    const double pc = mpc_lds(xc ? stN + S::PC * 8 + xcol[s2] : stN + S::ZS * 8);
+                    mpc_sts_if(xc, stN + S::PV * 8 + (xc ? xcol[s2] : 0), gtn);
+                    x[s2] = mpc_sel(ins[s2] == 1, u0, mpc_sel(ins[s2] == 2, u1, gtn + pc));
+                }
+            }
+            double m[2], cf[2], pcv[2], lu[3], gu[2];
+            auto load_b = [&](const unsigned st, const unsigned stp) {
+#pragma unroll
+                for (int s2 = 0; s2 < 2; s2++) {
+                    double e = fma(sg[s2], mpc_lds(st + eo[s2]), idv[s2]);
+                    e = fma(-mpc_lds(st + b0[s2]), mpc_lds(st + k0[s2]), e);
+                    e = fma(-mpc_lds(st + b1[s2]), mpc_lds(st + k1[s2]), e);
+                    m[s2] = e;
+                    const bool xc = xcol[s2] >= 0;
+                    cf[s2] = mpc_lds(xc ? st + (S::GT + NU) * 8 + xcol[s2] : st + S::ZS * 8);
+                    pcv[s2] = mpc_lds(xc ? st + S::PC * 8 + xcol[s2] : st + S::ZS * 8);
+                }
+                lu[0] = mpc_lds(st + S::LUU * 8);
+                lu[1] = mpc_lds(st + S::LUU * 8 + 8);
+                lu[2] = mpc_lds(st + S::LUU * 8 + 16);
+                gu[0] = mpc_lds(stp + S::GT * 8);  // gt_u of the NEXT stage of the sweep (k - 1)
+                gu[1] = mpc_lds(stp + S::GT * 8 + 8);
+            };
+            load_b(sbase + (N - 1) * SB, sbase + (N > 1 ? N - 2 : 0) * SB);
+#pragma unroll 1
+            for (int k = N - 1; k >= 0; k--) {
+                const unsigned st = sbase + k * SB;
+                const double m0 = m[0], m1 = m[1], c0 = cf[0], c1 = cf[1], p0 = pcv[0], p1 = pcv[1];
+                const double il00 = lu[0], l10 = lu[1], il11 = lu[2], u0 = gu[0], u1 = gu[1];
+                double d0, d1;
+                mpc_dmma(d0, d1, x[0], m0, c0, c1);
+                mpc_dmma(d0, d1, x[1], m1, d0, d1);
+                if (k > 0) load_b(st - SB, st - (k > 1 ? 2 : 1) * SB);  // next stage's entries: in flight under the products
+                mpc_sts_if(xcol[0] >= 0, st + S::PV * 8 + (xcol[0] >= 0 ? xcol[0] : 0), d0);
+                mpc_sts_if(xcol[1] >= 0, st + S::PV * 8 + (xcol[1] >= 0 ? xcol[1] : 0), d1);
+                // y = L_uu^-1 m_u: m_u sits in columns NX, NX + 1 of row 0
+                const double mu0 = __shfl_sync(FULL, (NX & 1) ? d1 : d0, NX >> 1);
+                const double mu1 = __shfl_sync(FULL, ((NX + 1) & 1) ? d1 : d0, (NX + 1) >> 1);
+                const double y0 = mu0 * il00;
+                const double y1 = (mu1 - l10 * y0) * il11;
+                mpc_sts_if(lane == 0, st + S::YV * 8, y0);
+                mpc_sts_if(lane == 0, st + S::YV * 8 + 8, y1);
+                // next row vector: q_k = pv_k + P_k c_k-1 in the state columns, gt_u of stage k - 1 in the input columns
+                x[0] = mpc_sel(ins[0] == 1, u0, mpc_sel(ins[0] == 2, u1, d0 + p0));
+                x[1] = mpc_sel(ins[1] == 1, u0, mpc_sel(ins[1] == 2, u1, d1 + p1));
+            }
+            __syncwarp();
+        }
+        // ---- forward: [dx_k+1 | du_k] = [c_k | 0] + [dx_k | f_k] Mf_k,  f = -L_uu^-T y ----
+        tables(true, eo, b0, k0, b1, k1, idv, sg);
+        double m[2], cf[2], fn[2];
+        auto load_f = [&](const unsigned st) {
+#pragma unroll
+            for (int s2 = 0; s2 < 2; s2++) {
+                double e = fma(sg[s2], mpc_lds(st + eo[s2]), idv[s2]);
+                e = fma(-mpc_lds(st + b0[s2]), mpc_lds(st + k0[s2]), e);
+                e = fma(-mpc_lds(st + b1[s2]), mpc_lds(st + k1[s2]), e);
+                m[s2] = e;
+                cf[s2] = mpc_lds(xcol[s2] >= 0 ? st + S::C * 8 + xcol[s2] : st + S::ZS * 8);
+            }
+        };
+        auto load_fvec = [&](const unsigned st) {  // f of stage st (y may have been written by the backward sweep above)
+            const double y0 = mpc_lds_v(st + S::YV * 8), y1 = mpc_lds_v(st + S::YV * 8 + 8);
+            const double il00 = mpc_lds(st + S::LUU * 8), l10 = mpc_lds(st + S::LUU * 8 + 8), il11 = mpc_lds(st + S::LUU * 8 + 16);
+            fn[1] = -(y1 * il11);
+            fn[0] = -((y0 + l10 * fn[1]) * il00);
+        };
+        {
+            const unsigned W = sbase + S::W_BASE * 8;
+            load_fvec(sbase);
+#pragma unroll
+            for (int s2 = 0; s2 < 2; s2++) {
+                const bool xc = xcol[s2] >= 0;
+                const double v = mpc_lds(xc ? W + S::W_DX0 * 8 + xcol[s2] : sbase + S::ZS * 8);
+                mpc_sts_if(xc, sbase + (S::DZN + NU) * 8 + (xc ? xcol[s2] : 0), v);
+                x[s2] = mpc_sel(ins[s2] == 1, fn[0], mpc_sel(ins[s2] == 2, fn[1], v));
+            }
+            load_f(sbase);
+            if (N > 1) load_fvec(sbase + SB);
+        }
+#pragma unroll 1
+        for (int k = 0; k < N; k++) {
+            const unsigned st = sbase + k * SB, stn = st + SB;
+            const double m0 = m[0], m1 = m[1], c0 = cf[0], c1 = cf[1], f0 = fn[0], f1 = fn[1];
+            double d0, d1;
+            mpc_dmma(d0, d1, x[0], m0, c0, c1);
+            mpc_dmma(d0, d1, x[1], m1, d0, d1);
+            if (k + 1 < N) {
+                load_f(stn);
+                if (k + 2 < N) load_fvec(stn + SB);
+            }
+            // dx_k+1 -> DZN of the next stage, du_k -> DZN of this stage
+#pragma unroll
+            for (int s2 = 0; s2 < 2; s2++) {
+                const double d = s2 ? d1 : d0;
+                mpc_sts_if(xcol[s2] >= 0, stn + (S::DZN + NU) * 8 + (xcol[s2] >= 0 ? xcol[s2] : 0), d);
+                mpc_sts_if(ins[s2] != 0, st + S::DZN * 8 + (ins[s2] == 2 ? 8 : 0), d);
+            }
+            x[0] = mpc_sel(ins[0] == 1, f0, mpc_sel(ins[0] == 2, f1, d0));
+            x[1] = mpc_sel(ins[1] == 1, f0, mpc_sel(ins[1] == 2, f1, d1));
         }
     }
     __syncthreads();
@@ -1341,7 +1557,7 @@ template <class CFG>
 MPC_DEV void riccati_solve_dense(double *sm, bool BACKWARD) {
     typedef SL<CFG> S;
     typedef RicIdx<CFG> R;
-    constexpr int N = CFG::N, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
+    constexpr int N = CFG::N, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
     double *W = sm + S::W_BASE;
     const int serial_tid = (int)W[S::W_STID];
     MPC_PHASE
@@ -1408,23 +1624,14 @@ MPC_DEV void riccati_solve_dense(double *sm, bool BACKWARD) {
         }
     }
     MPC_PHASE_END
-    MPC_PHASE
-    for (int it = tid; it < N * NX; it += NT) {
-        const int k = 1 + it / NX, i = it % NX;
-        double *st = sm + k * S::STRIDE;
-        double acc = st[S::PV + i];
-        for (int mm = 0; mm < NX; mm++) acc += st[S::P + trisym(i, mm)] * st[S::DZN + NU + mm];
-        st[S::PIN + i] = acc;
-    }
-    MPC_PHASE_END
 }
 
-// Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PIN.
+// Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PV.
 template <class CFG>
 MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
     typedef SL<CFG> S;
     typedef RicIdx<CFG> R;
-    constexpr int N = CFG::N, NX = CFG::NX, NU = CFG::NU, NE = R::NE, NT = MPC_NT;
+    constexpr int N = CFG::N, NX = CFG::NX, NU = CFG::NU, NE = R::NE;
     double *W = sm + S::W_BASE;
     const int serial_tid = (int)W[S::W_STID];
     MPC_PHASE
@@ -1507,17 +1714,7 @@ MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
         }
     }
     MPC_PHASE_END
-    // pi_k = P_k dx_k + pv_k  for k = 1..N, all in parallel
-    MPC_PHASE
-    for (int it = tid; it < N * NX; it += NT) {
-        const int k = 1 + it / NX, i = it % NX;
-        double *st = sm + k * S::STRIDE;
-        double acc = st[S::PV + i];
-#pragma unroll
-        for (int m = 0; m < NX; m++) acc += st[S::P + trisym(i, m)] * st[S::DZN + NU + m];
-        st[S::PIN + i] = acc;
-    }
-    MPC_PHASE_END
+    // the equality-multiplier target pi_k = P_k dx_k + pv_k is formed where it is consumed (the step phase PA of ipm_solve)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1536,17 +1733,10 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
     {
         double rs = 0.0, re = 0.0;
         for (int it = tid; it < (N + 1) * NZ; it += NT) {
-            // heavy variables (x, y, psi) first so that they spread over distinct threads
-            int k, i;
-            if (it < 3 * (N + 1)) {
-                k = it % (N + 1);
-                i = CFG::IX + it / (N + 1);
-            } else {
-                const int r = it - 3 * (N + 1);
-                k = r % (N + 1);
-                const int c = r / (N + 1);  // 0..NZ-4 over the remaining variables
-                i = (c < CFG::IX) ? c : c + 3;
-            }
+            // item = (variable slot v, stage k), stage fastest; the heavy variables (x, y, psi) take slots 0..2 so that they
+            // spread over distinct threads, the remaining variables follow in their own order
+            const int v = it / (N + 1), k = it - v * (N + 1);
+            const int i = (v < 3) ? CFG::IX + v : ((v - 3 < CFG::IX) ? v - 3 : v);
             if (k == N && i < NU) continue;
             double *st = sm + k * S::STRIDE;
             const int a = i - CFG::IX;  // 0,1,2 for x,y,psi
@@ -1694,6 +1884,15 @@ struct RowCtx {
     double a0, a1, a2;
 };
 
+// fmax() with the second operand known not to be NaN, as one compare + select (fmax proper carries NaN handling for both
+// operands: it was half of the row bodies' instructions).  Same value as fmax(v, floor) for every v, NaN included.
+MPC_HD double mpc_floor_at(double v, double floor) { return (v > floor) ? v : floor; }
+// acc = fmax(acc, v) for a running maximum that is never NaN itself (starts at 0, only ever takes a compared-greater value):
+// a NaN candidate is dropped, exactly as fmax drops it.
+MPC_HD void mpc_raise(double &acc, double v) {
+    if (v > acc) acc = v;
+}
+
 template <class CFG, int MODE>
 MPC_HD void row_body(double *st, int r, double cv, double cvn, RowCtx &c) {
     typedef SL<CFG> S;
@@ -1702,18 +1901,18 @@ MPC_HD void row_body(double *st, int r, double cv, double cvn, RowCtx &c) {
         double tt, l;
         if (c.first) {
             if (c.warm) {  // qp_solver_warm_start = 2: keep the previous QP's multipliers, re-centre the slacks
-                tt = fmax(cv, c.ws_thr);
-                l = fmax(st[S::LAM + r], c.ws_mu * mpc_rcp(tt));
+                tt = mpc_floor_at(cv, c.ws_thr);
+                l = mpc_floor_at(st[S::LAM + r], c.ws_mu * mpc_rcp(tt));  // the floor is finite: tt >= ws_thr > 0
             } else {
-                tt = fmax(cv, c.thr0);
+                tt = mpc_floor_at(cv, c.thr0);
                 l = c.mu0 * mpc_rcp(tt);
             }
         } else {
             const double t0 = st[S::T + r], l0 = st[S::LAM + r], ti = st[S::TINV + r];
             const double dt = cvn - t0;
             const double dl = (c.sigma_mu - st[S::CORR + r]) * ti - l0 * ti * cvn;
-            tt = fmax(t0 + c.alpha * dt, T_MIN);
-            l = fmax(l0 + c.alpha * dl, LAM_MIN);
+            tt = mpc_floor_at(t0 + c.alpha * dt, T_MIN);
+            l = mpc_floor_at(l0 + c.alpha * dl, LAM_MIN);
         }
         st[S::T + r] = tt;
         st[S::LAM + r] = l;
@@ -1726,7 +1925,8 @@ MPC_HD void row_body(double *st, int r, double cv, double cvn, RowCtx &c) {
         const double tt = st[S::T + r], l = st[S::LAM + r], ti = st[S::TINV + r];
         const double dt = cvn - tt;
         const double dl = -l * ti * cvn;                 // sigma mu = corr = 0
-        c.a0 = fmax(c.a0, fmax(-dt * ti, ti * cvn));     // -dl/lam = cvn/t
+        mpc_raise(c.a0, -dt * ti);                       // ratio test: max of -dt/t and -dl/lam = cvn/t
+        mpc_raise(c.a0, ti * cvn);
         c.a1 += l * dt + tt * dl;
         c.a2 += dt * dl;
         st[S::CORR + r] = dt * dl;
@@ -1734,7 +1934,8 @@ MPC_HD void row_body(double *st, int r, double cv, double cvn, RowCtx &c) {
         const double tt = st[S::T + r], l = st[S::LAM + r], ti = st[S::TINV + r];
         const double dt = cvn - tt;
         const double dl = (c.sigma_mu - st[S::CORR + r]) * ti - l * ti * cvn;
-        c.a0 = fmax(c.a0, fmax(-dt * ti, -dl * mpc_rcp(l)));
+        mpc_raise(c.a0, -dt * ti);
+        mpc_raise(c.a0, -dl * mpc_rcp(l));
     }
 }
 
@@ -1749,7 +1950,9 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
         c.a0 = c.a1 = c.a2 = 0.0;
         // boxes: both rows of variable i of stage k (x0 is fixed: no state box at node 0)
         for (int it = tid; it < N * NZ; it += NT) {
-            const int k = it / NZ, i = it - k * NZ;
+            // stage fastest: neighbouring lanes sit an odd number of doubles apart (the stage stride) -- variable fastest put
+            // lanes (k, i + 1) and (k + 1, i) on the same bank pair (46 % excess wavefronts in the row bodies)
+            const int i = it / N, k = it - i * N;
             if (k == 0 && i >= NU) continue;
             double *st = sm + k * S::STRIDE;
             const double lb = W[S::W_LB + i], ub = W[S::W_UB + i];
@@ -1795,6 +1998,12 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
 // Interior-point QP solve.  Returns the QP status (acados numbering: 0 ok, 2 max iter,
 // 3 min step, 4 NaN) -- uniform across the CTA.
 // ---------------------------------------------------------------------------------------------
+#if defined(__CUDACC__) && !defined(MPC_RICCATI_SERIAL) && !defined(MPC_RICCATI_LANES) && defined(MPC_SOLVE_MMA)
+#define MPC_RICCATI_SOLVE riccati_solve_mma  // measured alternative: pairs with riccati_factor_mma storing Kt in the L_xu slot
+#else
+#define MPC_RICCATI_SOLVE riccati_solve
+#endif
+
 template <class CFG>
 MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, double *res_out) {
     typedef SL<CFG> S;
@@ -1816,14 +2025,11 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
     // t = max(r, thr0), lam = mu0 / t; warm: see there)
     MPC_PHASE
     for (int it = tid; it < (N + 1) * NZ; it += NT) {
-        const int k = it / NZ, i = it - k * NZ;
+        const int i = it / (N + 1), k = it - i * (N + 1);  // stage fastest: bank-conflict free
         double *st = sm + k * S::STRIDE;
         st[S::DZ + i] = (k == 0 && i >= NU) ? W[S::W_DX0 + i - NU] : 0.0;
         st[S::DZN + i] = st[S::DZ + i];
-        if (i < NX) {
-            st[S::DPI + i] = 0.0;
-            st[S::PIN + i] = 0.0;
-        }
+        if (i < NX) st[S::DPI + i] = 0.0;
     }
     MPC_PHASE_END
 
@@ -1835,10 +2041,17 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
         if (iter > 0) {
             MPC_PHASE
             for (int it = tid; it < (N + 1) * NZ; it += NT) {
-                const int k = it / NZ, i = it - k * NZ;
+                const int i = it / (N + 1), k = it - i * (N + 1);  // stage fastest: bank-conflict free
                 double *st = sm + k * S::STRIDE;
                 if (!((k == 0 && i >= NU) || (k == N && i < NU))) st[S::DZ + i] += alpha * (st[S::DZN + i] - st[S::DZ + i]);
-                if (k >= 1 && i < NX) st[S::DPI + i] += alpha * (st[S::PIN + i] - st[S::DPI + i]);
+                if (k >= 1 && i < NX) {
+                    // Newton target of the equality multiplier, pi_k = P_k dx_k + pv_k (dx = the target's state part):
+                    // formed here, its only consumer, instead of in a phase of its own after every sweep
+                    double pin = st[S::PV + i];
+#pragma unroll
+                    for (int m = 0; m < NX; m++) pin += st[S::P + trisym(i, m)] * st[S::DZN + NU + m];
+                    st[S::DPI + i] += alpha * (pin - st[S::DPI + i]);
+                }
             }
             MPC_PHASE_END
             MPC_TICK(TK_PA)
@@ -1885,7 +2098,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
         }
         MPC_TICK(TK_FACTOR)
         if constexpr (CFG::BICYCLE) riccati_solve_dense<CFG>(sm, false);
-        else riccati_solve<CFG>(sm, false);
+        else MPC_RICCATI_SOLVE<CFG>(sm, false);
         MPC_TICK(TK_SOLVE)
         sigma_mu = 0.0;
         if (nc > 0) {
@@ -1912,7 +2125,7 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
             stage_accumulate<CFG, 1>(L, sm, sigma_mu);
             MPC_TICK(TK_ACC1)
             if constexpr (CFG::BICYCLE) riccati_solve_dense<CFG>(sm, true);
-            else riccati_solve<CFG>(sm, true);
+            else MPC_RICCATI_SOLVE<CFG>(sm, true);
             MPC_TICK(TK_SOLVE)
         }
         // ---- PF: step length to the boundary ----
@@ -2044,7 +2257,7 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
         // full step; multipliers <- QP multipliers (LAM already holds them)
         MPC_PHASE
         for (int it = tid; it < (N + 1) * NZ; it += NT) {
-            const int k = it / NZ, i = it - k * NZ;
+            const int i = it / (N + 1), k = it - i * (N + 1);  // stage fastest: bank-conflict free
             double *st = sm + k * S::STRIDE;
             if (!(k == N && i < NU)) st[S::Z + i] += st[S::DZ + i];
             if (iterates) {

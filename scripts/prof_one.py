@@ -7,7 +7,8 @@ from mpc_planner_b200 import binding, problem as pb, scenes
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 cfg = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
 spec = pb.CONFIGS[cfg]()
-base = scenes.make_scene_batch(spec, min(max(P // 8, 1), 32), 8, seed=1)
+distinct = len(sys.argv) > 3 and sys.argv[3] == "distinct"  # the bench batch: P / 8 distinct scenes
+base = scenes.make_scene_batch_chunked(spec, P // 8, 8, seed=1) if distinct else scenes.make_scene_batch(spec, min(max(P // 8, 1), 32), 8, seed=1)
 reps = (P + len(base["xinit"]) - 1) // len(base["xinit"])
 xinit = np.tile(base["xinit"], (reps, 1))[:P]
 x0 = np.tile(base["x0"], (reps, 1))[:P]

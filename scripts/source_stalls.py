@@ -6,7 +6,9 @@ import collections, csv, os, re, subprocess, sys, tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
-lib = os.path.join(ROOT, "mpc_planner_b200", "lib", "libmpcgpu.so")
+# optional: the library the capture ran and the source tree it was built from (defaults: the in-tree build and csrc/)
+lib = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "mpc_planner_b200", "lib", "libmpcgpu.so")
+SRC = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "mpc_planner_b200", "csrc")
 KEY = "sqp_kernelIN6mpcgpu6ConfigILi0ELi0ELi20ELi5ELi0ELi8ELi1ELi8ELi0ELi0E"
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL)
@@ -35,7 +37,7 @@ def functions_of(path):
     return out
 
 
-F = {f: functions_of(os.path.join(ROOT, "mpc_planner_b200", "csrc", f)) for f in ("sqp_core.cuh", "stage_functions.cuh")}
+F = {f: functions_of(os.path.join(SRC, f)) for f in ("sqp_core.cuh", "stage_functions.cuh")}
 
 
 def fn(key):
@@ -55,8 +57,11 @@ ia, isamp, iex, ib = hdr.index("Address"), hdr.index("# Samples"), hdr.index("In
 cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h and i != ib]
 base = int(data[0][ia], 16)
 tot, nb, st, executed = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter), collections.Counter()
+iti, iws, iwi = hdr.index("Thread Instructions Executed"), hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Ideal")
+winst, tinst, wsh, wshi = collections.Counter(), collections.Counter(), collections.Counter(), collections.Counter()
 for r in data:
     f = fn(table.get(int(r[ia], 16) - base))
+    winst[f] += int(r[iex]); tinst[f] += int(r[iti]); wsh[f] += int(r[iws] or 0); wshi[f] += int(r[iwi] or 0)
     tot[f] += int(r[isamp])
     nb[f] += int(r[isamp]) - int(r[ib])
     executed[f] += int(r[iex]) > 0
@@ -74,3 +79,10 @@ print("| function | share of non-barrier samples | top stall reasons | executed 
 for f, s in nb.most_common(16):
     top = ", ".join(f"{k} {100 * v // max(sum(st[f].values()), 1)} %" for k, v in st[f].most_common(4))
     print(f"| `{f}` | {100 * s / NB:.1f} % | {top} | {executed[f] * 16 / 1024:.1f} KB |")
+
+WI, WS = sum(winst.values()), sum(wsh.values())
+print(f"\nWarp instructions executed: {WI} ({sum(tinst.values()) / max(WI, 1):.1f} of 32 lanes active on average); shared-memory wavefronts: {WS} "
+      f"({100 * (WS - sum(wshi.values())) / max(WS, 1):.0f} % above the conflict-free count).\n")
+print("| function | warp instructions | share | active lanes | shared wavefronts | share | excess over ideal |\n|---|---|---|---|---|---|---|")
+for f, n in winst.most_common(18):
+    print(f"| `{f}` | {n} | {100 * n / WI:.1f} % | {tinst[f] / max(n, 1):.1f} | {wsh[f]} | {100 * wsh[f] / max(WS, 1):.1f} % | {100 * (wsh[f] - wshi[f]) / max(wsh[f], 1):.0f} % |")
