@@ -295,6 +295,9 @@ MPC_HD void linearize_part(const PA &pa, const Layout &L, double *st, const doub
     double z[NZ];
 #pragma unroll
     for (int i = 0; i < NZ; i++) z[i] = st[S::Z + i];
+#if defined(MPC_LIN_SKIP)  // development (scripts/profile_phases.py): leave parts out to time the others (results are garbage)
+    if ((MPC_LIN_SKIP >> (part < 2 ? part : 2)) & 1) return;
+#endif
     if (part == 0) {
         double Hp[S::NHP], g[NZ];
 #pragma unroll
@@ -666,8 +669,11 @@ MPC_DEV void riccati_factor(double *sm) {
                 }
                 Lx[i][0] = mx0 * il00;
                 Lx[i][1] = (mx1 - Lx[i][0] * l10) * il11;
-                st[S::LXU + i * NU] = Lx[i][0];
-                st[S::LXU + i * NU + 1] = Lx[i][1];
+                {   // stored for the vector sweeps: the feedback gain, transposed, Kt = L_xu L_uu^-1 (riccati_solve)
+                    const double kt1 = Lx[i][1] * il11;
+                    st[S::LXU + i * NU] = (Lx[i][0] - kt1 * l10) * il00;
+                    st[S::LXU + i * NU + 1] = kt1;
+                }
                 // vector sweep: pv_i = m_x,i - L_xu,i y,  m_x = gt_x + A' q,  A = I + E
                 double mx = st[S::GT + NU + i] + qv[i];
                 if (R::eidx(i) >= 0) {
@@ -951,9 +957,10 @@ MPC_DEV void riccati_factor_lanes(double *sm) {
             const double o0 = MPC_LV(Mc)[0] * il00;
             const double o1 = MPC_LV(Mc)[1] * il11 - MPC_LV(Mc)[0] * cx;
             {   // stores under simple predicates (no lane-dependent branches)
-                if (fl & 2) {  // vector lane: y;  x lanes: row of L_xu
-                    st[MPC_LV(sto)[0]] = o0;
-                    st[MPC_LV(sto)[0] + 1] = o1;
+                if (fl & 2) {  // vector lane: y;  x lanes: row of Kt = L_xu L_uu^-1 (what riccati_solve reads)
+                    const double s1 = vec ? o1 : o1 * il11;
+                    st[MPC_LV(sto)[0]] = vec ? o0 : (o0 - s1 * l10) * il00;
+                    st[MPC_LV(sto)[0] + 1] = s1;
                 }
                 if (fl & 4) {
                     st[S::LUU] = il00;
@@ -1231,16 +1238,12 @@ MPC_DEV void riccati_factor_mma(double *sm) {
                 const double L0 = t0[rt] * il00;
                 const double L1 = (t1[rt] - L0 * l10) * il11;
                 Lq[rt] = mpc_sel(q == 1, L1, mpc_sel(q == 0, L0, 0.0));
-                // what the vector sweeps read (riccati_solve_mma): x rows  Kt = L_xu L_uu^-1  (the feedback gain, transposed:
+                // what the vector sweeps read (riccati_solve): x rows  Kt = L_xu L_uu^-1  (the feedback gain, transposed:
                 // du = f - Kt' dx), vector row  y = L_uu^-1 m_u
-#if !defined(MPC_SOLVE_MMA)  // the single-thread sweeps (riccati_solve) read L_xu
-                mpc_sts_if(fx[rt] != 0, st + lx_off[rt], Lq[rt]);
-#else
                 const double K1 = L1 * il11;
                 const double K0 = (L0 - K1 * l10) * il00;
                 const bool yrow = (rt == VT) && is_vec;
                 mpc_sts_if(fx[rt] != 0, st + lx_off[rt], mpc_sel(yrow, Lq[rt], mpc_sel(q == 1, K1, K0)));
-#endif
             }
             // GEMM 3: Pt = Mt - L L'
 #pragma unroll
@@ -1626,6 +1629,10 @@ MPC_DEV void riccati_solve_dense(double *sm, bool BACKWARD) {
     MPC_PHASE_END
 }
 
+// (Measured alternative: the same sweeps with every run of consecutive doubles moved 16 bytes at a time -- LDS.128 / STS.128
+// where the odd stage stride leaves the address aligned, parity-specialised (odd, even) stage pairs: a third fewer loads, no
+// gain (bench batch 6.11 -> 6.16 ms, one control step 0.640 -> 0.648 ms): the lone thread waits on its FP64 chain, not on the
+// load instructions.)
 // Backward vector sweep + forward sweep for the gradient GT:  writes DZN (all nodes) and PV.
 template <class CFG>
 MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
@@ -1636,7 +1643,7 @@ MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
     const int serial_tid = (int)W[S::W_STID];
     MPC_PHASE
     if (tid == serial_tid) {
-        // backward: m = gt + BA'(pv+ + P+ c);  y = Luu^-1 m_u;  pv = m_x - Lxu y
+        // backward: m = gt + BA'(pv+ + P+ c);  pv = m_x - Kt m_u  (Kt = L_xu L_uu^-1, stored by the factorisation);  y = Luu^-1 m_u
         // (BACKWARD = false: riccati_factor_lanes already ran this sweep for the current gradient)
         if (BACKWARD) {
         double pv[NX];
@@ -1658,6 +1665,8 @@ MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
                 if (R::bnz(l, 0)) m0 += st[S::BB + l * NU + 0] * q[l];
                 if (R::bnz(l, 1)) m1 += st[S::BB + l * NU + 1] * q[l];
             }
+            // y = L_uu^-1 m_u is only stored (the forward sweep starts from it): the recursion itself continues from m_u
+            // through the gain, pv = m_x - Kt m_u (= m_x - L_xu y), three links of the dependent chain shorter
             const double y0 = m0 * st[S::LUU];
             const double y1 = (m1 - st[S::LUU + 1] * y0) * st[S::LUU + 2];
             st[S::YV] = y0;
@@ -1670,12 +1679,12 @@ MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
                     for (int l = 0; l < NX; l++)
                         if (R::enz(l, R::eidx(i) >= 0 ? R::eidx(i) : 0)) mx += st[S::BE + l * NE + (R::eidx(i) >= 0 ? R::eidx(i) : 0)] * q[l];
                 }
-                pv[i] = mx - st[S::LXU + i * NU] * y0 - st[S::LXU + i * NU + 1] * y1;
+                pv[i] = mx - st[S::LXU + i * NU] * m0 - st[S::LXU + i * NU + 1] * m1;
                 st[S::PV + i] = pv[i];
             }
         }
         }
-        // forward: du = -Luu^-T (y + Lxu' dx);  dx+ = c + B du + A dx
+        // forward: du = -Luu^-T y - Kt' dx;  dx+ = c + B du + A dx
         double dx[NX];
 #pragma unroll
         for (int i = 0; i < NX; i++) {
@@ -1686,26 +1695,28 @@ MPC_DEV void riccati_solve(double *sm, bool BACKWARD) {
         for (int k = 0; k < N; k++) {
             double *st = sm + k * S::STRIDE;
             double *stn = st + S::STRIDE;
-            double w0 = st[S::YV], w1 = st[S::YV + 1];
+            // du = f - Kt' dx with f = -L_uu^-T y (independent of dx: off the chain);  dx+ = (c + A dx) + B du, the bracket in
+            // parallel with du
+            const double il00 = st[S::LUU], l10 = st[S::LUU + 1], il11 = st[S::LUU + 2];
+            const double f1 = -(st[S::YV + 1] * il11);
+            const double f0 = -((st[S::YV] + l10 * f1) * il00);
+            double du0 = f0, du1 = f1;
 #pragma unroll
             for (int l = 0; l < NX; l++) {
-                w0 += st[S::LXU + l * NU] * dx[l];
-                w1 += st[S::LXU + l * NU + 1] * dx[l];
+                du0 -= st[S::LXU + l * NU] * dx[l];
+                du1 -= st[S::LXU + l * NU + 1] * dx[l];
             }
-            const double il00 = st[S::LUU], l10 = st[S::LUU + 1], il11 = st[S::LUU + 2];
-            const double k1 = w1 * il11;
-            const double k0 = (w0 - l10 * k1) * il00;
-            st[S::DZN] = -k0;
-            st[S::DZN + 1] = -k1;
+            st[S::DZN] = du0;
+            st[S::DZN + 1] = du1;
             double dxn[NX];
 #pragma unroll
             for (int i = 0; i < NX; i++) {
                 double acc = st[S::C + i] + dx[i];
-                if (R::bnz(i, 0)) acc -= st[S::BB + i * NU] * k0;
-                if (R::bnz(i, 1)) acc -= st[S::BB + i * NU + 1] * k1;
 #pragma unroll
                 for (int c = 0; c < NE; c++)
                     if (R::enz(i, c)) acc += st[S::BE + i * NE + c] * dx[R::ecol(c)];
+                if (R::bnz(i, 0)) acc += st[S::BB + i * NU] * du0;
+                if (R::bnz(i, 1)) acc += st[S::BB + i * NU + 1] * du1;
                 dxn[i] = acc;
                 stn[S::DZN + NU + i] = acc;
             }
@@ -2216,6 +2227,10 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     for (int sq = 0; sq < L.n_sqp; sq++) {
         // preparation: linearise every stage at the current iterate
         MPC_PHASE
+        // (stage, part) items packed over consecutive threads.  Measured alternative: one part per warp (cost in warp 0, dynamics
+        // in warp 1, constraint quarters in warps 2 and 3) so that the divergent cost and dynamics paths of warp 0 do not run one
+        // after the other -- cost + dynamics did drop from 5.7k to 3.4k cycles per linearisation, but the constraint part
+        // executed from its own code copy went from 0.5k to 7k: 6.15 -> 6.28 .. 6.42 ms on the bench batch.
         for (int it = tid; it < 6 * N; it += NT) {
             const int part = it / N, k = it - part * N;  // same part in neighbouring threads
             ParamT<pt_stride(N)> pa{pt, k};

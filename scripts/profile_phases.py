@@ -5,9 +5,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from mpc_planner_b200 import build, binding, problem as pb, scenes
 
-lib_prof = os.path.join(build.LIB_DIR, "libmpcgpu_prof.so")
+# PROF_TAG / PROF_FLAGS: extra development flags for the profiled build (e.g. -DMPC_LIN_SKIP=1)
+tag = os.environ.get("PROF_TAG", "")
+lib_prof = os.path.join(build.LIB_DIR, "libmpcgpu_prof%s.so" % tag)
 if "--build" in sys.argv or not os.path.exists(lib_prof):
-    cmd = [build.nvcc_path()] + build.NVCC_FLAGS + ["-DMPC_PROFILE", "-I" + os.path.join(build.ROOT, "include"), "-o", lib_prof, os.path.join(build.CSRC, "mpcgpu.cu")]
+    cmd = [build.nvcc_path()] + build.NVCC_FLAGS + ["-DMPC_PROFILE"] + os.environ.get("PROF_FLAGS", "").split() + ["-I" + os.path.join(build.ROOT, "include"), "-o", lib_prof, os.path.join(build.CSRC, "mpcgpu.cu")]
     subprocess.check_call(cmd, cwd=build.CSRC)
     if "--build" in sys.argv:
         sys.exit(0)
@@ -24,6 +26,6 @@ xt, ut, info, best = s.solve(xi, x0, par)
 names = ["lin", "assemble(mirror)", "ipm_init", "PA", "PB rows", "acc0", "reduce", "factor", "solve", "PD rows", "acc1", "PF rows", "sqp step", "final"]
 prof = ut.reshape(P, -1)[:, :16]
 tot = prof[:, :14].sum(axis=1)
-print(f"{cfg} P={P}: mean total cycles {tot.mean():.0f}; mean qp_iter {np.mean([i['qp_iter'] for i in info]):.1f}")
+print(f"{cfg} P={P}{tag}: mean total cycles {tot.mean():.0f}; mean qp_iter {np.mean([i['qp_iter'] for i in info]):.1f}; mean sqp_iter {np.mean([i['sqp_iter'] for i in info]):.2f}")
 for i, n in enumerate(names):
     print(f"  {n:18s} {prof[:, i].mean():12.0f} cycles  {100 * prof[:, i].mean() / tot.mean():5.1f}%")
