@@ -2227,10 +2227,12 @@ MPC_DEV void sqp_solve_cta(const Layout &L, double *sm, const double *xinit, con
     for (int sq = 0; sq < L.n_sqp; sq++) {
         // preparation: linearise every stage at the current iterate
         MPC_PHASE
-        // (stage, part) items packed over consecutive threads.  Measured alternative: one part per warp (cost in warp 0, dynamics
-        // in warp 1, constraint quarters in warps 2 and 3) so that the divergent cost and dynamics paths of warp 0 do not run one
-        // after the other -- cost + dynamics did drop from 5.7k to 3.4k cycles per linearisation, but the constraint part
-        // executed from its own code copy went from 0.5k to 7k: 6.15 -> 6.28 .. 6.42 ms on the bench batch.
+        // (stage, part) items packed over consecutive threads: warp 0 holds the cost lanes and 12 of the dynamics lanes, whose
+        // divergent paths run one after the other (cost 3.4k + dynamics 2.2k = 5.7k cycles per linearisation, cfg 2; the
+        // constraint quarters hide behind them).  Measured alternatives that keep cost and dynamics in different warps -- one
+        // part per warp, or the slot order cost / constraints / dynamics / constraints -- both LOSE: the two long paths running
+        // concurrently take 9-10k cycles (6.13 -> 6.28 .. 6.42 ms on the bench batch); the phase is bound by something the two
+        // streams share (instruction fetch of ~20 KB of once-per-linearisation code is the suspect), not by the lanes.
         for (int it = tid; it < 6 * N; it += NT) {
             const int part = it / N, k = it - part * N;  // same part in neighbouring threads
             ParamT<pt_stride(N)> pa{pt, k};
