@@ -65,6 +65,8 @@ inline mpc_cdouble exp(mpc_cdouble a) { g_flops.trans++; return mpc_cdouble(std:
 inline mpc_cdouble log(mpc_cdouble a) { g_flops.trans++; return mpc_cdouble(std::log(a.v)); }
 inline mpc_cdouble sin(mpc_cdouble a) { g_flops.trans++; return mpc_cdouble(std::sin(a.v)); }
 inline mpc_cdouble cos(mpc_cdouble a) { g_flops.trans++; return mpc_cdouble(std::cos(a.v)); }
+inline mpc_cdouble tan(mpc_cdouble a) { g_flops.trans++; return mpc_cdouble(std::tan(a.v)); }
+inline mpc_cdouble atan(mpc_cdouble a) { g_flops.trans++; return mpc_cdouble(std::atan(a.v)); }
 inline mpc_cdouble erf(mpc_cdouble a) { g_flops.trans++; return mpc_cdouble(std::erf(a.v)); }
 inline mpc_cdouble fmod(mpc_cdouble a, mpc_cdouble b) { g_flops.div++; return mpc_cdouble(std::fmod(a.v, b.v)); }
 inline void sincos(mpc_cdouble a, mpc_cdouble *s, mpc_cdouble *c) { g_flops.trans += 2; s->v = std::sin(a.v); c->v = std::cos(a.v); }
