@@ -159,7 +159,9 @@ struct SL {
     static constexpr int DZN = DPI + NX;        // Newton target (primal); the multiplier target P dx + pv is formed on the fly
     // MIRROR work space of the CTA-parallel Jacobi: the working copy of the block lives in the T / TINV / CORR rows (dead
     // between QPs) when they hold NZ x NZ doubles, else in an extra area behind the stage image (bicycle with few rows)
-    static constexpr int ZS = DZN + NZ;         // one double that is 0.0 for the whole solve (set at load time, never written): the
+    static constexpr int DZS = DZN + NZ;        // the QP iterate after the step of the current IPM iteration: written by the row phase that
+                                                // takes the step, read by the accumulations, which copy it back into DZ (see rows_phase)
+    static constexpr int ZS = DZS + NZ;         // one double that is 0.0 for the whole solve (set at load time, never written): the
                                                 // tensor-core sweep points its structurally absent loads here instead of predicating them
     static constexpr int MIR_EXTRA = (3 * NROW >= NZ * NZ) ? 0 : NZ * NZ;
     static constexpr int MW = MIR_EXTRA ? ZS + 1 : T;
@@ -1759,7 +1761,7 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
                 if (k < N) {
                     rg = st[S::GR + i];
 #pragma unroll
-                    for (int j = 0; j < NZ; j++) rg += st[S::H + trisym(i, j)] * st[S::DZ + j];
+                    for (int j = 0; j < NZ; j++) rg += st[S::H + trisym(i, j)] * st[S::DZS + j];
                     const double *stn = sm + (k + 1) * S::STRIDE;
                     // (BA' dpi+)_i with A = I + E
                     if (i < NU) {
@@ -1774,7 +1776,7 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
                         }
                     }
                 } else {
-                    rg = L.reg_epsilon * st[S::DZ + i];  // H_N = eps I, g_N = 0
+                    rg = L.reg_epsilon * st[S::DZS + i];  // H_N = eps I, g_N = 0
                 }
                 if (k >= 1 && i >= NU) rg -= st[S::DPI + i - NU];
             }
@@ -1855,16 +1857,17 @@ MPC_DEV void stage_accumulate(const Layout &L, double *sm, double sigma_mu) {
             }
             st[S::GT + i] = gt;
             if (MODE == 0) {
+                st[S::DZ + i] = st[S::DZS + i];  // the stepped iterate becomes the iterate (every read of this phase goes to DZS)
                 st[S::GD + i] = gd;
                 if (!(k == 0 && i >= NU)) upd_max(rs, fabs(rg));  // x0 is eliminated
                 if (k < N && i >= NU) {                            // equality residual of row i - NU
                     const int r = i - NU;
                     const double *stn = sm + (k + 1) * S::STRIDE;
-                    double acc = st[S::C + r] - stn[S::DZ + NU + r];
+                    double acc = st[S::C + r] - stn[S::DZS + NU + r];
 #pragma unroll
-                    for (int u = 0; u < NU; u++) acc += st[S::BB + r * NU + u] * st[S::DZ + u];
-                    acc += st[S::DZ + NU + r] + st[S::BE + r * S::NE] * st[S::DZ + NU + 2] + st[S::BE + r * S::NE + 1] * st[S::DZ + NU + 3];
-                    if (S::NE > 2) acc += st[S::BE + r * S::NE + (S::NE > 2 ? 2 : 0)] * st[S::DZ + NU + 4];
+                    for (int u = 0; u < NU; u++) acc += st[S::BB + r * NU + u] * st[S::DZS + u];
+                    acc += st[S::DZS + NU + r] + st[S::BE + r * S::NE] * st[S::DZS + NU + 2] + st[S::BE + r * S::NE + 1] * st[S::DZS + NU + 3];
+                    if (S::NE > 2) acc += st[S::BE + r * S::NE + (S::NE > 2 ? 2 : 0)] * st[S::DZS + NU + 4];
                     upd_max(re, fabs(acc));
                 }
             }
@@ -1959,15 +1962,36 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
     {
         RowCtx c = ctx;
         c.a0 = c.a1 = c.a2 = 0.0;
+        // RP_UPDATE also TAKES the primal / equality-multiplier step of the previous iteration (it used to be a phase of its own):
+        //   dz <- dz + alpha (dzn - dz),   dpi <- dpi + alpha (P dxn + pv - dpi)
+        // The stepped dz goes to the shadow array DZS -- other threads of this phase still read the un-stepped DZ of the same
+        // stage (general rows: x, y, psi) and step it on the fly -- and the accumulation phase that follows reads DZS and
+        // copies it back.  Same expressions as the separate phase had (iterates agree to rounding: the compiler contracts them differently).
+        const bool step = (MODE == RP_UPDATE) && !c.first;
+        constexpr int NK = (MODE == RP_UPDATE) ? N + 1 : N;  // the update also visits the terminal node (no rows there)
         // boxes: both rows of variable i of stage k (x0 is fixed: no state box at node 0)
-        for (int it = tid; it < N * NZ; it += NT) {
+        for (int it = tid; it < NK * NZ; it += NT) {
             // stage fastest: neighbouring lanes sit an odd number of doubles apart (the stage stride) -- variable fastest put
             // lanes (k, i + 1) and (k + 1, i) on the same bank pair (46 % excess wavefronts in the row bodies)
-            const int i = it / N, k = it - i * N;
-            if (k == 0 && i >= NU) continue;
+            const int i = it / NK, k = it - i * NK;
             double *st = sm + k * S::STRIDE;
+            double v = st[S::DZ + i];
+            const double vn = st[S::DZN + i];
+            if (MODE == RP_UPDATE) {
+                if (step && !((k == 0 && i >= NU) || (k == N && i < NU))) v += c.alpha * (vn - v);
+                st[S::DZS + i] = v;
+                if (step && k >= 1 && i < CFG::NX) {
+                    // Newton target of the equality multiplier, pi_k = P_k dx_k + pv_k (dx = the target's state part)
+                    double pin = st[S::PV + i];
+#pragma unroll
+                    for (int m = 0; m < CFG::NX; m++) pin += st[S::P + trisym(i, m)] * st[S::DZN + NU + m];
+                    st[S::DPI + i] += c.alpha * (pin - st[S::DPI + i]);
+                }
+                if (k == N) continue;
+            }
+            if (k == 0 && i >= NU) continue;
             const double lb = W[S::W_LB + i], ub = W[S::W_UB + i];
-            const double z = st[S::Z + i], v = st[S::DZ + i], vn = st[S::DZN + i];
+            const double z = st[S::Z + i];
             // rows are relaxed by qp_relax (see mpcgpu.h): an interior exists even for rows pinned at their bound.
             // One copy of the row body for both sides (run-time loop): lower z - lb + v, upper ub - z - v = -(z - ub + v)
 #pragma unroll 1
@@ -1982,11 +2006,26 @@ MPC_DEV void rows_phase(const Layout &L, double *sm, RowCtx ctx) {
             const int k = 1 + it / (NH > 0 ? NH : 1), j = it - (k - 1) * NH;
             double *st = sm + k * S::STRIDE;
             const double j0 = st[S::JR + 3 * j], j1 = st[S::JR + 3 * j + 1], j2 = st[S::JR + 3 * j + 2], rh = st[S::RH + j];
-            double cv = rh + j0 * st[S::DZ + CFG::IX] + j1 * st[S::DZ + CFG::IY] + j2 * st[S::DZ + CFG::IPSI];
-            double cvn = rh + j0 * st[S::DZN + CFG::IX] + j1 * st[S::DZN + CFG::IY] + j2 * st[S::DZN + CFG::IPSI];
+            const double nx = st[S::DZN + CFG::IX], ny = st[S::DZN + CFG::IY], np = st[S::DZN + CFG::IPSI];
+            double cv = 0.0;
+            if (MODE == RP_UPDATE) {  // the other modes only use the row value at the Newton target
+                double dx = st[S::DZ + CFG::IX], dy = st[S::DZ + CFG::IY], dp = st[S::DZ + CFG::IPSI];
+                if (step) {
+                    dx += c.alpha * (nx - dx);
+                    dy += c.alpha * (ny - dy);
+                    dp += c.alpha * (np - dp);
+                }
+                cv = rh + j0 * dx + j1 * dy + j2 * dp;
+            }
+            double cvn = rh + j0 * nx + j1 * ny + j2 * np;
             if (CFG::ANY_SLACK_ROWS && row_has_slack<CFG>(j)) {
-                cv += st[S::DZ + (CFG::HAS_SLACK ? CFG::ISLACK : 0)];
-                cvn += st[S::DZN + (CFG::HAS_SLACK ? CFG::ISLACK : 0)];
+                const double ns = st[S::DZN + (CFG::HAS_SLACK ? CFG::ISLACK : 0)];
+                if (MODE == RP_UPDATE) {
+                    double ds = st[S::DZ + (CFG::HAS_SLACK ? CFG::ISLACK : 0)];
+                    if (step) ds += c.alpha * (ns - ds);
+                    cv += ds;
+                }
+                cvn += ns;
             }
             row_body<CFG, MODE>(st, 2 * NZ + j, cv, cvn, c);
         }
@@ -2048,26 +2087,8 @@ MPC_DEV int ipm_solve(const Layout &L, double *sm, int *iters_out, bool warm, do
     int status = 0, iter = 0;
     double alpha = 0.0, sigma_mu = 0.0;
     for (;; iter++) {
-        // ---- PA: primal / equality-multiplier step of the previous iteration ----
-        if (iter > 0) {
-            MPC_PHASE
-            for (int it = tid; it < (N + 1) * NZ; it += NT) {
-                const int i = it / (N + 1), k = it - i * (N + 1);  // stage fastest: bank-conflict free
-                double *st = sm + k * S::STRIDE;
-                if (!((k == 0 && i >= NU) || (k == N && i < NU))) st[S::DZ + i] += alpha * (st[S::DZN + i] - st[S::DZ + i]);
-                if (k >= 1 && i < NX) {
-                    // Newton target of the equality multiplier, pi_k = P_k dx_k + pv_k (dx = the target's state part):
-                    // formed here, its only consumer, instead of in a phase of its own after every sweep
-                    double pin = st[S::PV + i];
-#pragma unroll
-                    for (int m = 0; m < NX; m++) pin += st[S::P + trisym(i, m)] * st[S::DZN + NU + m];
-                    st[S::DPI + i] += alpha * (pin - st[S::DPI + i]);
-                }
-            }
-            MPC_PHASE_END
-            MPC_TICK(TK_PA)
-        }
-        // ---- PB: rows: (init | step) of t, lam; 1/t; residual pieces ----
+        // (PA, the primal / equality-multiplier step of the previous iteration, is taken inside the row phase below)
+        // ---- PA + PB: step of dz, dpi; rows: (init | step) of t, lam; 1/t; residual pieces ----
         {
             RowCtx c;
             c.first = (iter == 0);
