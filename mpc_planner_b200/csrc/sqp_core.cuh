@@ -1281,7 +1281,7 @@ MPC_DEV void riccati_factor_mma(double *sm) {
 // stage ahead of the chain.  Same algebra as the serial sweeps up to rounding.  Why it loses: the chain is short (two DMMA),
 // but a warp issues in order and forming the entries on the fly costs ~17 LDS + 6 FMA per stage on top of the products --
 // ~50 warp instructions per stage and sweep against the lone thread's ~70 cheap ones, ~310 cycles against ~170.  Storing the
-// closed-loop matrix (25 doubles per stage) would fix that; the stage image has 4 doubles left.
+// closed-loop matrix (25 doubles per stage) would fix that; the stage image has 2 doubles left at four solves per SM.
 // ---------------------------------------------------------------------------------------------
 MPC_DEV double mpc_lds_v(unsigned addr) {  // load of data written earlier in the same function by another lane
     double v;

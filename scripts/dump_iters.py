@@ -1,3 +1,5 @@
+"""Development aid (profiles/r02_tail.md): IPM / SQP iteration counts of every solve of the bench batch, for n_sqp = 1, 2, 3, 4, 6, 10
+(cumulative counts: how well the first QPs predict the length of a solve).  Writes gpurun_out/iters_by_nsqp.json."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
