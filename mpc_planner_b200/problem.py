@@ -136,6 +136,9 @@ class ProblemSpec:
     qp_ws_mu: float = 1e-5
     qp_relax: float = 1e-7
     res_eq_fail: float = 1e-2  # acados_solver_interface.cpp:176
+    # model bounds that differ from the model class's table, by variable name: {"w": (-2.0, 2.0), ...}  (the reference's
+    # DynamicsModel carries lower_bound / upper_bound as plain data, solver_model.py:129-167)
+    bounds_override: Dict[str, Tuple[float, float]] = field(default_factory=dict)
 
     # ---- model_map ----
     @property
@@ -161,6 +164,14 @@ class ProblemSpec:
     @property
     def nh(self) -> int:
         return sum(c for _, c in self.constraints)
+
+    def model_bounds(self):
+        """(lower, upper) over z = [u; x]: the model class's table with `bounds_override` applied by variable name."""
+        lo, up = list(_MODELS[self.model]["lower"]), list(_MODELS[self.model]["upper"])
+        names = self.inputs + self.states
+        for name, (l, u) in self.bounds_override.items():
+            lo[names.index(name)], up[names.index(name)] = float(l), float(u)
+        return lo, up
 
     def model_map(self) -> Dict[str, list]:
         """name -> ["x"|"u", index in z, lower, upper]  (solver_model.py:117-128 save_map)."""
@@ -309,7 +320,7 @@ class ProblemSpec:
         d.n_con_modules = len(self.constraints)
         for i, ((k, n), p0) in enumerate(zip(self.constraints, self.constraint_first_param())):
             d.con_kind[i], d.con_count[i], d.con_param[i] = k, n, p0
-        lo, up = _MODELS[self.model]["lower"], _MODELS[self.model]["upper"]
+        lo, up = self.model_bounds()
         for i in range(self.nz):
             d.lower_bound[i], d.upper_bound[i] = lo[i], up[i]
         d.n_sqp, d.qp_iter_max, d.qp_tol = self.n_sqp, self.qp_iter_max, self.qp_tol
@@ -386,7 +397,7 @@ class GeneratedSpec(ProblemSpec):
         d.weigh_velocity = 0
         d.n_con_modules = 1
         d.con_kind[0], d.con_count[0], d.con_param[0] = CON_GENERATED, self.nh, 0
-        lo, up = _MODELS[self.model]["lower"], _MODELS[self.model]["upper"]
+        lo, up = self.model_bounds()
         for i in range(self.nz):
             d.lower_bound[i], d.upper_bound[i] = lo[i], up[i]
         d.n_sqp, d.qp_iter_max, d.qp_tol = self.n_sqp, self.qp_iter_max, self.qp_tol
@@ -407,6 +418,18 @@ class GeneratedSpec(ProblemSpec):
             else:
                 raise ValueError("no oracle restatement for this generated stack")
         return d
+
+
+def second_order_unicycle_goal(**kw) -> "GeneratedSpec":
+    """`SecondOrderUnicycleModel` (solver_model.py:170-190: states x, y, psi, v; no generator script of the reference instantiates
+    it) under the Goal stack of configuration_lmpcc.  It runs as its `ContouringSecondOrderUnicycleModel` twin with the spline
+    state idle: the reference's own Python gives the same l, h and the same first four rows of f for the two models at every
+    point (tests/golden `second_order_unicycle`), the fifth row (spline' = v) feeds nothing back, and the spline bound
+    [-1, 10000] cannot bind -- so (x, y, psi, v, a, w) of the 5-state solve are the 4-state problem's solution (to the interior-point
+    tolerance: the barrier of that never-active bound is the only place the spline value enters).  The model's own bounds
+    (:177-178) replace the contouring model's."""
+    return GeneratedSpec.load("lmpcc_goal", bounds_override={"a": (-2.0, 2.0), "w": (-2.0, 2.0), "x": (-200.0, 200.0), "y": (-200.0, 200.0),
+                                                             "psi": (-math.pi * 4, math.pi * 4), "v": (-2.0, 3.0)}, **kw)
 
 
 # ---- the BASELINE.json configs (SURVEY.md section 8 table) ----

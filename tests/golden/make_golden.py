@@ -62,6 +62,7 @@ from solver_model import (  # noqa: E402
     BicycleModel2ndOrder,
     ContouringSecondOrderUnicycleModel,
     ContouringSecondOrderUnicycleModelWithSlack,
+    SecondOrderUnicycleModel,
 )
 from util.parameters import Parameters  # noqa: E402
 
@@ -263,6 +264,28 @@ def main(M=24):
         z = random_z(bm, rng)
         bs.append(dict(z=z.tolist(), f=[float(v) for v in bm.continuous_model(z[bm.nu:], z[: bm.nu])]))
     out["bicycle"] = dict(samples=bs, lower_bound=list(map(float, bm.lower_bound)), upper_bound=list(map(float, bm.upper_bound)))
+
+    # SecondOrderUnicycleModel (solver_model.py:170-190; no generator script of the reference instantiates it): the Goal stack of
+    # configuration_lmpcc evaluated on it AND on ContouringSecondOrderUnicycleModel at the same point extended by an arbitrary
+    # spline state -- the reference's own numbers show the 4-state problem is the 5-state one with the spline state idle
+    m4, m5 = SecondOrderUnicycleModel(), ContouringSecondOrderUnicycleModel()
+    rng = np.random.default_rng(4242)
+    so = []
+    for _ in range(12):
+        _, modules, settings = build("lmpcc_goal")
+        params = Parameters(); define_parameters(modules, params, settings); settings["params"] = params
+        pmap = {k: int(v) for k, v in params._params.items()}
+        z4 = random_z(m4, rng)
+        z5 = np.append(z4, rng.uniform(0.0, 24.0))
+        p = random_params(pmap, rng)
+        rec = dict(z4=z4.tolist(), z5=z5.tolist(), p=p.tolist())
+        for tag, mdl, z in (("4", m4, z4), ("5", m5, z5)):
+            rec["cost" + tag] = float(objective(modules, z, p, mdl, settings, 1))
+            rec["h" + tag] = [float(v) for v in constraints(modules, z, p, mdl, settings, 1)]
+            rec["f" + tag] = [float(v) for v in mdl.continuous_model(z[mdl.nu:], z[: mdl.nu])]
+        so.append(rec)
+    out["second_order_unicycle"] = dict(samples=so, states=m4.states, inputs=m4.inputs, lower_bound=list(map(float, m4.lower_bound)),
+                                        upper_bound=list(map(float, m4.upper_bound)))
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stage_functions.json")
     with open(path, "w") as f:

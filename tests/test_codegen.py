@@ -276,3 +276,64 @@ def test_sqp_kernel_on_the_emitted_goal_stack_solves_like_the_oracle():
         if oinfo[i]["exit_code"] == 1:
             goal = par[i, 0, [pm["goal_x"], pm["goal_y"]]]
             assert np.linalg.norm(xt[i, -1, :2] - goal) < np.linalg.norm(xt[i, 0, :2] - goal)
+
+
+# ---- SecondOrderUnicycleModel (solver_model.py:170-190) as the Goal stack with an idle spline state --------------------------
+def test_second_order_unicycle_is_the_contouring_model_with_an_idle_spline_state(golden):
+    """The reference's OWN Python (fixture `second_order_unicycle`, tests/golden/make_golden.py): Goal-stack cost, constraints and
+    the first four rows of f are the same numbers on SecondOrderUnicycleModel and on ContouringSecondOrderUnicycleModel at the
+    point extended by ANY spline value; the fifth row is v.  The emitted Goal stack reproduces the 4-state model's numbers."""
+    g = golden["second_order_unicycle"]
+    assert g["states"] == ["x", "y", "psi", "v"] and g["inputs"] == ["a", "w"]
+    lib = gen_lib("lmpcc_goal")
+    for s in g["samples"]:
+        assert s["cost4"] == s["cost5"] and s["h4"] == s["h5"] and s["f4"] == s["f5"][:4]
+        assert s["f5"][4] == s["z5"][5]  # spline' = v
+        out = gen_eval(lib, np.array(s["z5"]), np.array(s["p"]))
+        np.testing.assert_allclose(out["cost"][0], s["cost4"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(out["h"][0], s["h4"], rtol=1e-11, atol=1e-10)
+    spec = pb.second_order_unicycle_goal()
+    lo, up = spec.model_bounds()
+    assert lo[:6] == g["lower_bound"] and up[:6] == g["upper_bound"]  # the 4-state model's own bounds (:177-178)
+    assert pb.GeneratedSpec.load("lmpcc_goal").model_bounds()[0][1] == -0.8  # the contouring model's table is untouched
+
+
+def test_second_order_unicycle_goal_solve_ignores_the_spline_state():
+    """The 5-state solve IS the 4-state problem's solution: started from spline = 0 and from spline = 7.3 (initial state and warm
+    start shifted alike) the kernel (host emulation) returns the same (x, y, psi, v) and (a, w) trajectories to the solver's
+    tolerance, and the oracle agrees with it."""
+    from oracle import oracle
+    from tests.util import same_status
+
+    gspec = pb.second_order_unicycle_goal(oracle_objective=pb.OBJ_GOAL)
+    lib = _generated_emulation(gspec)
+    xinit, x0, params = goal_batch(gspec, 3, seed=11)
+    N, nz, nu = gspec.N, gspec.nz, gspec.nu
+    xinit2, x02 = xinit.copy(), x0.copy().reshape(3, N + 1, nz)
+    xinit2[:, 4] += 7.3
+    x02[:, :, nu + 4] += 7.3
+    x02 = x02.reshape(3, -1)
+    xt, ut, info = emu.solve_batch(gspec, xinit, x0, params, library=lib)
+    xt2, ut2, info2 = emu.solve_batch(gspec, xinit2, x02, params, library=lib)
+
+    class OracleView:
+        N, nx, nu, nz, npar, n_sqp = gspec.N, gspec.nx, gspec.nu, gspec.nz, gspec.npar, gspec.n_sqp
+
+        @staticmethod
+        def desc():
+            return gspec.desc(for_oracle=True)
+
+    oxt, out, oinfo = oracle.solve_batch(OracleView, xinit, x0, params)
+    n_ok = 0
+    for i in range(3):
+        assert same_status(info[i], oinfo[i]) and same_status(info[i], info2[i])
+        if oinfo[i]["exit_code"] == 1:
+            n_ok += 1
+            # to the interior-point tolerance (qp_tol = 1e-5; observed <= 1.2e-5): the barrier of the spline state's never-active
+            # bound [-1, 10000] is the only place its value enters
+            np.testing.assert_allclose(xt[i][:, :4], xt2[i][:, :4], rtol=0, atol=1e-4)
+            np.testing.assert_allclose(ut[i], ut2[i], rtol=0, atol=1e-4)
+            np.testing.assert_allclose(xt2[i][:, 4] - xt[i][:, 4], 7.3, rtol=0, atol=1e-4)
+            np.testing.assert_allclose(xt[i], oxt[i], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(ut[i], out[i], rtol=1e-6, atol=1e-6)
+    assert n_ok >= 2
