@@ -19,6 +19,35 @@ extern "C" void emu_mirror_stats(long *calls, long *slow) { *calls = g_mirror_ca
 extern "C" long emu_mirror_general_count() { return g_mirror_general; }
 // round-robin schedule of the parallel Jacobi (csrc/sqp_core.cuh tournament_pair): pair j of round r for m indices
 extern "C" void emu_tournament_pair(int m, int r, int j, int *p, int *q) { tournament_pair(m, r, j, *p, *q); }
+// compare + select forms of fmax used by the row bodies (csrc/sqp_core.cuh)
+extern "C" double emu_floor_at(double v, double floor) { return mpc_floor_at(v, floor); }
+extern "C" double emu_raise(double acc, double v) { mpc_raise(acc, v); return acc; }
+#ifndef MPCGPU_GENERATED_REGISTRY  // (the shipped stacks; a per-problem emulation has its own Config list)
+// rows of h that linearisation thread `q` of 4 evaluates for a stack (kind, count) x 3: every row exactly once over q = 0..3
+template <class CFG>
+static void quarter_rows(int q, int *hit) {
+    double z[CFG::NZ] = {0}, hv[CFG::NH > 0 ? CFG::NH : 1], J[CFG::NH > 0 ? 3 * CFG::NH : 1], w[CFG::NH > 0 ? CFG::NH : 1] = {0}, Hx[6] = {0};
+    for (int j = 0; j < CFG::NH; j++) hv[j] = -12345.0;
+    Layout L = {};
+    L.p_ego_disc_offset = -1;
+    std::vector<double> par(4096, 0.5);
+    ParamP pa{par.data()};
+    for (int m = 0; m < 3; m++) L.con_param[m] = 16 + 200 * m;
+    L.p_ego_disc_radius = 1;
+    stage_constraints<CFG, true>(pa, L, z, hv, J, w, Hx, 0, CFG::NH, q, 4);
+    for (int j = 0; j < CFG::NH; j++) hit[j] += (hv[j] != -12345.0);
+}
+extern "C" int emu_quarter_rows(int cfg, int q, int *hit) {
+    switch (cfg) {
+        case 1: quarter_rows<cfg_basic_n20_o4>(q, hit); return cfg_basic_n20_o4::NH;
+        case 2: quarter_rows<cfg_tmpc_n20_o8>(q, hit); return cfg_tmpc_n20_o8::NH;
+        case 3: quarter_rows<cfg_tmpc_decomp_n30_o12>(q, hit); return cfg_tmpc_decomp_n30_o12::NH;
+        case 4: quarter_rows<cfg_safe_horizon_n20>(q, hit); return cfg_safe_horizon_n20::NH;
+        case 5: quarter_rows<cfg_tmpc_gauss_n20_o8>(q, hit); return cfg_tmpc_gauss_n20_o8::NH;
+    }
+    return -1;
+}
+#endif
 
 template <class CFG>
 static int solve_cfg(const mpcgpu_problem_desc &d, int P, const double *xinit, const double *x0, const double *params,

@@ -184,3 +184,39 @@ def test_structural_sparsity_assumed_by_the_riccati_sweeps(golden, name):
                 c = {2: 0, 3: 1}.get(j, -1)
                 if c < 0 or not enz(l, c):
                     assert E[l, j] == 0.0
+
+
+def test_compare_select_forms_equal_fmax():
+    """The row bodies use `(v > floor) ? v : floor` and `if (v > acc) acc = v` where they used fmax (half of their instructions):
+    same value for every input the callers can produce -- any v, NaN included, against a non-NaN floor / running maximum."""
+    import ctypes
+    import math
+
+    L = emu.lib()
+    for f in (L.emu_floor_at, L.emu_raise):
+        f.restype = ctypes.c_double
+        f.argtypes = [ctypes.c_double, ctypes.c_double]
+    vals = [0.0, -0.0, 1e-300, -1e-300, 1.0, -1.0, 1e-10, 1e-16, 3.5, -7.25, 1e300, -1e300, math.inf, -math.inf, math.nan]
+    libm = ctypes.CDLL("libm.so.6")  # C fmax: the function the kernel source called
+    libm.fmax.restype = ctypes.c_double
+    libm.fmax.argtypes = [ctypes.c_double, ctypes.c_double]
+    same = lambda a, b: (a != a and b != b) or a == b
+    for v in vals:
+        for c in vals:
+            if c == c:
+                assert same(L.emu_floor_at(v, c), libm.fmax(v, c)), (v, c)
+                assert same(L.emu_raise(c, v), libm.fmax(c, v)), (c, v)
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+def test_constraint_rows_are_dealt_to_the_four_linearisation_threads_exactly_once(cfg):
+    """linearize_part gives thread q of a stage share q of 4 of EVERY constraint block (stage_constraints(..., q, 4)): over
+    q = 0..3 each row of h is evaluated exactly once, whatever the block sizes (4; 8 + 8; 12 + 12 + 12; 24)."""
+    import ctypes
+
+    L = emu.lib()
+    hit = (ctypes.c_int * 64)()
+    nh = -1
+    for q in range(4):
+        nh = L.emu_quarter_rows(cfg, q, hit)
+    assert nh > 0 and list(hit[:nh]) == [1] * nh and not any(hit[nh:])
