@@ -4,8 +4,9 @@
 // Replaces, for the hot path, what the reference delegates to acados (SQP-RTI), HPIPM (IPM QP) and
 // BLASFEO: per RTI iteration  linearise all stages (threads = stage x function part)  ->
 // MIRROR-regularise  ->  Mehrotra predictor-corrector interior point on the stage-structured QP
-// (threads = stage x inequality row) with a Riccati factorisation (one thread, register resident;
-// DESIGN.md 4 lists the cooperative variants that were measured)  ->  full step.
+// (threads = stage x inequality row) with a Riccati factorisation (device: one warp on the FP64 tensor-core path,
+// riccati_factor_mma; host emulation: one thread) and single-thread vector sweeps through the stored feedback gain
+// (DESIGN.md 4 lists the variants that were built and measured)  ->  full step.
 //
 // Structure: the routine is a sequence of CTA "phases".  Inside a phase every thread works on data
 // written by earlier phases and writes a disjoint part of shared memory; phases are separated by
